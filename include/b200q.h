@@ -1,0 +1,176 @@
+/*
+ * b200q.h — C ABI of libb200quant.so: the B200-native (sm_100a) numeric hot path of
+ * AyoubMDL/onnx_quantize v0.3.0.
+ *
+ * Every entry point replaces a NumPy function of the reference (cited per function as
+ * file:line under /root/reference/src/onnx_quantize/).  Conventions:
+ *   - extern "C", plain pointers and sizes, no C++/torch types;
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name ends in
+ *     `_host`; nothing is allocated behind the caller's back: scratch memory is passed in
+ *     (`workspace`, sized by the matching `*_workspace_bytes` query);
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it and
+ *     returns without synchronising (except the `_host` variants, which synchronise the stream
+ *     before returning because they hand results back in host memory);
+ *   - return value: 0 ok, <0 argument/support/runtime error (b200q_last_error() has the text),
+ *     >0 numeric status (B200Q_NOT_POSITIVE_DEFINITE);
+ *   - thread-safe per stream; no state is kept between calls.
+ *
+ * Weights are (K = in_channels, N = out_channels) row-major float32 — the ONNX MatMul layout
+ * that reaches the reference plugin as `w.const_value.numpy()` (core/_algorithms/rtn.py:41).
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_VERSION 100 /* 0.1.0 */
+
+typedef void* b200q_stream_t; /* cudaStream_t */
+
+enum b200q_status {
+  B200Q_OK = 0,
+  B200Q_ERR_INVALID_ARG = -1,
+  B200Q_ERR_UNSUPPORTED = -2,
+  B200Q_ERR_WORKSPACE = -3,
+  B200Q_ERR_CUDA = -4,
+  B200Q_NOT_POSITIVE_DEFINITE = 1 /* Cholesky hit a non-positive pivot: gptq.py:143-150 */
+};
+
+/* core/_dtypes.py:33-41 (QuantType) */
+enum b200q_qtype { B200Q_INT4 = 0, B200Q_UINT4 = 1, B200Q_INT8 = 2, B200Q_UINT8 = 3 };
+
+/* core/_qconfig.py:31-36 (QuantizationStrategy) */
+enum b200q_strategy { B200Q_TENSOR = 0, B200Q_CHANNEL = 1, B200Q_GROUP = 2 };
+
+/* Where the integer codes go.
+ *   KN_BYTES     one byte per element, (K,N) row-major — the array `_rtn_quantize` returns
+ *                (rtn.py:107-109; ml_dtypes int4/uint4 are 1 byte per element unpacked).
+ *   PACKED_FLAT  "layout A": the INT4/UINT4 initializer bytes, ceil(K*N/2) bytes, flat row-major,
+ *                low nibble first, odd tail padded with 0 (core/_pack.py:8-22).
+ *   MATMUL_NBITS "layout B": com.microsoft.MatMulNBits operands (qrules/_common.py:65-123):
+ *                B (N, K/gs, gs*bits/8) u8, scales (N, K/gs) f32, zero points (N, ceil(G/2)) u8
+ *                nibble-packed along g (pad 0x8) for 4-bit with G>1, else (N, G) u8.
+ */
+enum b200q_layout { B200Q_KN_BYTES = 0, B200Q_PACKED_FLAT = 1, B200Q_MATMUL_NBITS = 2 };
+
+/* Hessian contraction precision on the tcgen05 tensor cores. */
+enum b200q_precision { B200Q_TF32 = 0, B200Q_TF32X3 = 1 };
+
+/* GPTQ update rule: REFERENCE reproduces gptq.py:198-208 as written (reads the zero triangle of
+ * the upper factor: no error propagation); PROPAGATE is GPTQ as published. */
+enum b200q_gptq_mode { B200Q_GPTQ_REFERENCE = 0, B200Q_GPTQ_PROPAGATE = 1 };
+
+int b200q_version(void);
+const char* b200q_status_string(int status);
+const char* b200q_last_error(void); /* thread-local text of the last failing call */
+
+/* ---------------------------------------------------------------------------------------------
+ * RTN weight quantization — replaces `_rtn_quantize` (core/_algorithms/rtn.py:54-109), i.e.
+ * `_preprocess_array` (utils.py:6-26), `_compute_min_max` (utils.py:42-69),
+ * `_compute_min_max_mse` (utils.py:140-239), `_compute_qparams` (utils.py:242-299),
+ * `_quantize_array_from_qparams` (utils.py:72-79), `_post_process_array` (utils.py:29-39), and
+ * with layout != KN_BYTES also `_pack_4bitx2` (core/_pack.py:8-22) or
+ * `_prepare_for_matmul_nbits` (qrules/_common.py:65-123).
+ *
+ *   W            (K,N) row-major f32
+ *   group_size   rows per group for B200Q_GROUP (must divide K; -1 or >K means K), else ignored
+ *   clip_ratio   python float of the reference; applied in f32; ignored when mse != 0
+ *                (utils.py:332-344 overwrites the clipped range)
+ *   out_codes    see enum b200q_layout
+ *   out_scale    f32, one per parameter row: 1 (TENSOR) / N (CHANNEL) / N*K/gs (GROUP, index
+ *                n*(K/gs)+g — identical memory for `(N*G,1)` of rtn.py and `(N,G)` of layout B)
+ *   out_zp       one byte per parameter row (two's complement for signed types), same order;
+ *                for MATMUL_NBITS the packed form described above
+ *   out_mse_info optional (may be NULL): int32[2] = {early-stop index i*, OR of the rows'
+ *                "improved at step i" masks}; only written when mse != 0
+ * ------------------------------------------------------------------------------------------ */
+size_t b200q_rtn_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t group_size, int mse);
+
+int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                       int64_t group_size, int symmetric, int reduce_range, double clip_ratio,
+                       int mse, int layout, void* out_codes, float* out_scale, void* out_zp,
+                       int32_t* out_mse_info, void* workspace, size_t workspace_bytes,
+                       b200q_stream_t stream);
+
+/* Per-candidate error sums of the MSE search (utils.py:197-224) for every parameter row:
+ * out_err is f32 [20][rows].  Diagnostic/test entry point used to pin the summation order. */
+int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                          int64_t group_size, int symmetric, int reduce_range, float* out_err,
+                          void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/* Quantization range per parameter row — replaces `_compute_min_max` (utils.py:42-69) and, with
+ * mse != 0, `_compute_min_max_mse` (utils.py:140-239).  out_min/out_max hold one f32 per row
+ * (zero included).  qtype/symmetric/reduce_range are only used by the MSE search. */
+int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                     int64_t group_size, int symmetric, int reduce_range, double clip_ratio, int mse,
+                     float* out_min, float* out_max, void* workspace, size_t workspace_bytes,
+                     b200q_stream_t stream);
+
+/* Codes from given per-row parameters — replaces `_quantize_array_from_qparams` (utils.py:72-79).
+ * scale/zp are laid out as b200q_rtn_quantize writes them; out_codes is KN_BYTES. */
+int b200q_quantize_with_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                                int64_t group_size, int symmetric, int reduce_range,
+                                const float* scale, const void* zp, void* out_codes,
+                                b200q_stream_t stream);
+
+/* scale / zero-point from ranges — replaces `_compute_qparams` (utils.py:242-299) as called by
+ * calibration (core/_calibration/calibrate.py:276).  rmin/rmax/out_* hold n entries. */
+int b200q_qparams(const float* rmin, const float* rmax, int64_t n, int qtype, int symmetric,
+                  int reduce_range, float* out_scale, void* out_zp, b200q_stream_t stream);
+
+/* (f32(q) - f32(zp)) * scale — replaces `_dequantize_array` (utils.py:102-137) with
+ * preprocess=True: codes are KN_BYTES, scale/zp are laid out as b200q_rtn_quantize writes them. */
+int b200q_dequantize(const void* codes, int64_t K, int64_t N, int qtype, int strategy,
+                     int64_t group_size, const float* scale, const void* zp, float* out,
+                     b200q_stream_t stream);
+
+/* int32 bias quantization — replaces `_quantize_bias` (rtn.py:112-138).
+ * out_scale[i] = weight_scale[i or 0] * input_scale; out_q = clip(rint(bias/out_scale)). */
+int b200q_quantize_bias(const float* bias, int64_t n, const float* weight_scale,
+                        int64_t n_weight_scale, float input_scale, int32_t* out_q,
+                        float* out_scale, b200q_stream_t stream);
+
+/* Stand-alone packers for codes that already exist as KN_BYTES. */
+int b200q_pack4_flat(const void* codes, int64_t n_elements, void* out, b200q_stream_t stream);
+/* Inverse of b200q_pack4_flat — replaces `_unpack_4bitx2` (core/_pack.py:25-38): n_elements
+ * bytes, each holding one nibble (low nibble first). */
+int b200q_unpack4_flat(const void* packed, int64_t n_elements, void* out_codes,
+                       b200q_stream_t stream);
+int b200q_pack_matmul_nbits(const void* codes, int64_t K, int64_t N, int64_t group_size, int bits,
+                            const void* zp_rows, void* out_B, void* out_zp, b200q_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Activation range calibration — replaces `MinMaxCalibrator.collect`
+ * (core/_calibration/minmax.py:40-64): global min and max of one activation batch.
+ *   minmax_batch  f32[2] = {min, max} of x[0..n)
+ * The running update (min/max or EMA) and `compute_range` (minmax.py:66-87) are
+ * b200q_minmax_merge below so that one launch folds any number of batches in batch order.
+ * ------------------------------------------------------------------------------------------ */
+size_t b200q_minmax_workspace_bytes(int64_t n);
+int b200q_minmax_reduce(const float* x, int64_t n, float* minmax_batch, void* workspace,
+                        size_t workspace_bytes, b200q_stream_t stream);
+/* state f32[2] (valid iff *state_valid != 0) <- fold `n_batches` (min,max) pairs in order:
+ * momentum == 0: running min / max (minmax.py:63-64); else EMA m*old + (1-m)*cur (minmax.py:55-60) */
+int b200q_minmax_merge(float* state, int32_t* state_valid, const float* batch_pairs,
+                       int64_t n_batches, double momentum, b200q_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GPTQ
+ * ------------------------------------------------------------------------------------------ */
+/* H <- beta*H + alpha * XᵀX — replaces `_accumulate_hessian` (core/_algorithms/gptq.py:246-260)
+ * with alpha = 2/num_samples, beta = n/(n+added).  X is (T,K) row-major f32 (tokens x in_channels),
+ * H is (K,K) f32.  Runs on tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM). */
+size_t b200q_hessian_workspace_bytes(int64_t T, int64_t K, int precision);
+int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, float beta,
+                             float* H, int precision, void* workspace, size_t workspace_bytes,
+                             b200q_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */

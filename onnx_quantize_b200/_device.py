@@ -1,0 +1,63 @@
+"""torch plumbing around the C ABI: device buffers, streams, workspace.  Nothing numeric lives here.
+
+PyTorch is used only as the owner of device memory and streams; the product kernels are in
+libb200quant.so.  Every helper raises when no CUDA device is available — there is no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "onnx_quantize_b200 needs a CUDA device (NVIDIA B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def to_device_f32(x, *, name: str = "array") -> torch.Tensor:
+    """numpy array / torch tensor → contiguous float32 CUDA tensor (no copy if already one)."""
+    dev = require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        if not a.flags.writeable:   # torch.from_numpy warns on read-only views; the data is only read
+            a = a.copy() if a.size < (1 << 20) else np.require(a, requirements="W")
+        t = torch.from_numpy(a)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if t.device.type != "cuda":
+        t = t.to(dev, non_blocking=True)
+    return t.contiguous()
+
+
+_WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(nbytes: int) -> torch.Tensor:
+    """A reusable scratch buffer per (device, stream); grows on demand, never shrinks."""
+    dev = require_cuda()
+    key = (dev.index, stream_ptr())
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _WORKSPACES.clear()

@@ -1,0 +1,106 @@
+"""ctypes binding of libb200quant.so (the C ABI declared in include/b200q.h).
+
+There is deliberately no fallback: if the shared library has not been built
+(``python __graft_entry__.py`` / ``onnx_quantize_b200/csrc/build.py``) or no CUDA device is
+present, every numeric entry point of this package raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200quant.so")
+
+# enums of include/b200q.h
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
+NOT_POSITIVE_DEFINITE = 1
+QTYPE = {"int4": 0, "uint4": 1, "int8": 2, "uint8": 3}
+STRATEGY = {"tensor": 0, "channel": 1, "group": 2}
+LAYOUT = {"kn": 0, "packed_flat": 1, "matmul_nbits": 2}
+PRECISION = {"tf32": 0, "tf32x3": 1}
+GPTQ_MODE = {"reference": 0, "propagate": 1}
+
+
+class B200QuantError(RuntimeError):
+    """A libb200quant call failed (CUDA error, workspace, unsupported configuration)."""
+
+
+_lock = threading.Lock()
+_lib = None
+
+_i64, _i32, _f32, _f64 = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double
+_ptr, _sz = ctypes.c_void_p, ctypes.c_size_t
+
+_SIGNATURES = {
+    "b200q_version": (ctypes.c_int, []),
+    "b200q_status_string": (ctypes.c_char_p, [_i32]),
+    "b200q_last_error": (ctypes.c_char_p, []),
+    "b200q_rtn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32]),
+    "b200q_rtn_quantize": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _i32,
+                                   _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "b200q_mse_error_table": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _ptr, _ptr,
+                                      _sz, _ptr]),
+    "b200q_row_ranges": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _ptr,
+                                 _ptr, _ptr, _sz, _ptr]),
+    "b200q_quantize_with_qparams": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _ptr,
+                                            _ptr, _ptr, _ptr]),
+    "b200q_qparams": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
+    "b200q_dequantize": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "b200q_quantize_bias": (_i32, [_ptr, _i64, _ptr, _i64, _f32, _ptr, _ptr, _ptr]),
+    "b200q_pack4_flat": (_i32, [_ptr, _i64, _ptr, _ptr]),
+    "b200q_unpack4_flat": (_i32, [_ptr, _i64, _ptr, _ptr]),
+    "b200q_pack_matmul_nbits": (_i32, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "b200q_minmax_workspace_bytes": (_sz, [_i64]),
+    "b200q_minmax_reduce": (_i32, [_ptr, _i64, _ptr, _ptr, _sz, _ptr]),
+    "b200q_minmax_merge": (_i32, [_ptr, _ptr, _ptr, _i64, _f64, _ptr]),
+}
+_OPTIONAL_SIGNATURES = {
+    "b200q_hessian_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "b200q_hessian_accumulate": (_i32, [_ptr, _i64, _i64, _f32, _f32, _ptr, _i32, _ptr, _sz, _ptr]),
+}
+
+
+def exported_symbols():
+    """Names include/b200q.h declares; used by the CPU test that the library exports them all."""
+    return sorted(list(_SIGNATURES) + list(_OPTIONAL_SIGNATURES))
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(`python -c 'import __graft_entry__ as g; g.build()'` at the repo root). "
+                "onnx_quantize_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in {**_SIGNATURES, **_OPTIONAL_SIGNATURES}.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                if name in _OPTIONAL_SIGNATURES:
+                    continue
+                raise ImportError(f"{LIB_PATH} does not export {name}; rebuild it") from None
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "libb200quant call") -> int:
+    """0 → ok; <0 → raise; >0 → numeric status handed back to the caller."""
+    if status >= 0:
+        return status
+    lib = load()
+    text = lib.b200q_last_error().decode() or lib.b200q_status_string(status).decode()
+    if status == ERR_INVALID_ARG:
+        raise ValueError(f"{what}: {text}")
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {text}")
+    raise B200QuantError(f"{what}: {text}")

@@ -1,0 +1,110 @@
+"""MinMax activation calibrator on the GPU — mirrors the reference's
+``core/_calibration/minmax.py`` (``MinMaxCalibrator`` :11-87).
+
+``collect`` launches one streaming min/max reduction per batch and appends the resulting
+(min, max) pair to a device-side list; nothing is synchronised or copied back until
+``compute_range`` (or ``.data``) is read, at which point all pending pairs are folded in batch
+order by one kernel — running min/max for ``momentum == 0`` (reference :63-64), the EMA
+``m·old + (1−m)·cur`` in float32 otherwise (reference :55-60).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from onnx_quantize_b200 import _device as dev
+from onnx_quantize_b200 import device_api as D
+from onnx_quantize_b200.core._calibration.base import CalibrationData, Calibrator
+
+logger = logging.getLogger(__name__)
+
+_PAIR_CHUNK = 64   # device slots for pending per-batch pairs; folded when full
+
+
+class _TensorState:
+    def __init__(self, device):
+        self.state = torch.zeros((2,), dtype=torch.float32, device=device)
+        self.valid = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.pairs = torch.empty((_PAIR_CHUNK, 2), dtype=torch.float32, device=device)
+        self.pending = 0
+
+
+class _LazyData(dict):
+    """``calibrator.data``: name → CalibrationData, materialised from the device on access."""
+
+    def __init__(self, owner: "MinMaxCalibrator"):
+        super().__init__()
+        self._owner = owner
+
+    def __getitem__(self, name):
+        self._owner._sync(name)
+        return super().__getitem__(name)
+
+    def values(self):
+        for name in list(self):
+            self._owner._sync(name)
+        return super().values()
+
+    def items(self):
+        for name in list(self):
+            self._owner._sync(name)
+        return super().items()
+
+
+class MinMaxCalibrator(Calibrator):
+    """Tracks the global minimum / maximum of every named activation tensor.
+
+    Args:
+        momentum: EMA factor in [0, 1); 0 means strict running min/max.
+    """
+
+    def __init__(self, momentum: float = 0.0):
+        super().__init__()
+        assert 0 <= momentum < 1, "Momentum must be in the range [0, 1)."
+        self.momentum = momentum
+        self.data = _LazyData(self)
+        self._dev: dict[str, _TensorState] = {}
+        logger.debug(f"Initialized MinMaxCalibrator with momentum={momentum}")
+
+    # -- device side ------------------------------------------------------------------------
+    def _fold(self, st: _TensorState) -> None:
+        if st.pending:
+            D.minmax_merge(st.state, st.valid, st.pairs[: st.pending], self.momentum)
+            st.pending = 0
+
+    def collect(self, name: str, array) -> None:
+        """Fold one activation batch (numpy array or CUDA tensor) into the statistics of ``name``."""
+        x = dev.to_device_f32(array)
+        st = self._dev.get(name)
+        if st is None:
+            st = self._dev[name] = _TensorState(x.device)
+            dict.__setitem__(self.data, name, CalibrationData(None, None))
+        if st.pending == _PAIR_CHUNK:
+            self._fold(st)
+        D.minmax_reduce(x.reshape(-1), st.pairs[st.pending])
+        st.pending += 1
+
+    def device_range(self, name: str) -> torch.Tensor:
+        """f32[2] = (min, max) on the device, all collected batches folded; no host sync."""
+        if name not in self._dev:
+            raise KeyError(f"No calibration data collected for '{name}'")
+        st = self._dev[name]
+        self._fold(st)
+        return st.state
+
+    # -- host side --------------------------------------------------------------------------
+    def _sync(self, name: str) -> None:
+        if name in self._dev:
+            lo, hi = self.device_range(name).cpu().numpy()
+            entry = dict.__getitem__(self.data, name)
+            entry.min_val, entry.max_val = np.float32(lo), np.float32(hi)
+
+    def compute_range(self, name: str) -> tuple[np.ndarray, np.ndarray]:
+        """(min, max) with zero included, as 0-d float32 arrays (reference minmax.py:66-87)."""
+        if name not in self._dev:
+            raise KeyError(f"No calibration data collected for '{name}'")
+        d = self.data[name]
+        return (np.array(np.minimum(d.min_val, 0), dtype=np.float32),
+                np.array(np.maximum(d.max_val, 0), dtype=np.float32))

@@ -1,0 +1,180 @@
+// mse_generic.cuh — exact MSE shrink-grid search (utils.py:140-239) for every layout the fused
+// kernel does not cover: any group size, CHANNEL, TENSOR.
+//
+// One thread evaluates one (parameter row, candidate) pair and accumulates the error in exactly
+// the order NumPy uses on the reference's array layout (pinned by oracle/c_sumorder.c):
+//     GROUP with G > 1 : rows are C-contiguous         -> pairwise_sum(n = gs)
+//     CHANNEL, G == 1  : rows are an F-ordered view    -> r = e0; r += e1; ... sequential in k
+//       (N == 1 makes that view contiguous            -> pairwise)
+//     TENSOR           : axis=None over the flat (K,N)  -> pairwise_sum(n = K*N)
+// A warp holds 32 adjacent output channels of one candidate, so loads are 128-byte runs.
+#pragma once
+
+#include "common.cuh"
+#include "rtn_fused.cuh"
+#include "rtn_generic.cuh"
+
+namespace b200q {
+
+struct ErrFn {
+  const float* w;     // first element of the row
+  int64_t stride;     // element stride inside the row
+  float scale;
+  int zp, qmin, qmax;
+  __device__ __forceinline__ float operator()(int64_t i) const {
+    float v = __ldg(w + i * stride);
+    float d = __fsub_rn(dequant_code(quant_code(v, scale, zp, qmin, qmax), zp, scale), v);
+    return pow_norm(fabsf(d));
+  }
+};
+
+// numpy/_core/src/umath/loops_utils.h.src::pairwise_sum (PW_BLOCKSIZE 128, unroll 8)
+template <class F>
+__device__ float pairwise_sum(const F& f, int64_t off, int64_t n) {
+  if (n < 8) {
+    float res = -0.0f;
+    for (int64_t i = 0; i < n; ++i) res = __fadd_rn(res, f(off + i));
+    return res;
+  } else if (n <= 128) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = f(off + j);
+    int64_t i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], f(off + i + j));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, f(off + i));
+    return res;
+  } else {
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    float a = pairwise_sum(f, off, n2);
+    float b = pairwise_sum(f, off + n2, n - n2);
+    return __fadd_rn(a, b);
+  }
+}
+
+template <class F>
+__device__ float sequential_sum(const F& f, int64_t n) {
+  float r = f(0);
+  for (int64_t i = 1; i < n; ++i) r = __fadd_rn(r, f(i));
+  return r;
+}
+
+// grid = (ceil(cols/32), G), block = (32, 20).  For TENSOR cols = 1, G = 1.
+// err is f32 [20][rows].
+static __global__ void __launch_bounds__(32 * kMseCandidates) mse_error_table_kernel(
+    const float* __restrict__ W, RowMap m, QSpec qs, const unsigned int* __restrict__ enc_min,
+    const unsigned int* __restrict__ enc_max, float* __restrict__ err,
+    const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  const int cand = threadIdx.y;
+  const bool tensor = m.strategy == B200Q_TENSOR;
+  const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int64_t g = blockIdx.y;
+  const int64_t cols = tensor ? 1 : m.N;
+  if (n >= cols) return;
+  const int64_t row = tensor ? 0 : n * m.G + g;
+  const int64_t rows = m.rows();
+  // starting range with clip_ratio = 1.0 (utils.py:188), zero included (utils.py:66-67)
+  const float lo0 = fminf(ordered_to_float(enc_min[row]), 0.0f);
+  const float hi0 = fmaxf(ordered_to_float(enc_max[row]), 0.0f);
+  const float p = kShrink[cand];
+  const QParam qp = qparam_from_range(__fmul_rn(p, lo0), __fmul_rn(p, hi0), qs);
+  ErrFn f;
+  f.scale = qp.scale; f.zp = qp.zp; f.qmin = qs.qmin; f.qmax = qs.qmax;
+  float e;
+  if (tensor) {
+    f.w = W; f.stride = 1;
+    e = pairwise_sum(f, 0, m.K * m.N);
+  } else {
+    f.w = W + g * m.gs * m.N + n; f.stride = m.N;
+    const bool pairwise = (m.strategy == B200Q_GROUP && m.G > 1) || m.N == 1;
+    e = pairwise ? pairwise_sum(f, 0, m.gs) : sequential_sum(f, m.gs);
+  }
+  err[(int64_t)cand * rows + row] = e;
+}
+
+// Per row: the "improved at step i" mask of the strict-< running minimum (utils.py:225-231).
+static __global__ void mse_row_masks_kernel(const float* __restrict__ err, int64_t rows,
+                                     unsigned int* __restrict__ masks,
+                                     unsigned int* __restrict__ or_mask,
+                                     const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int mask = 0;
+  if (r < rows) {
+    float best = FLT_MAX;
+    for (int i = 0; i < kMseCandidates; ++i) {
+      float e = err[(int64_t)i * rows + r];
+      if (e < best) { best = e; mask |= 1u << i; }
+    }
+    masks[r] = mask;
+  }
+  unsigned int any = __reduce_or_sync(0xffffffffu, mask);
+  if ((threadIdx.x & 31) == 0 && any) atomicOr(or_mask, any);
+}
+
+// Global early stop (utils.py:232-237): the counter is incremented at every step at which NO row
+// improved and is never reset; the loop ends after the step at which it reaches `patience`.
+__device__ __forceinline__ int mse_stop_index(unsigned int or_mask) {
+  int stalls = 0;
+  for (int i = 0; i < kMseCandidates; ++i) {
+    if (!((or_mask >> i) & 1u)) ++stalls;
+    if (stalls >= kMsePatience) return i;
+  }
+  return kMseCandidates - 1;
+}
+
+// masks + global stop index -> best candidate per row -> (scale, zp).
+static __global__ void mse_finalize_kernel(const unsigned int* __restrict__ masks,
+                                    const unsigned int* __restrict__ or_mask_p,
+                                    const unsigned int* __restrict__ enc_min,
+                                    const unsigned int* __restrict__ enc_max, int64_t rows, QSpec qs,
+                                    float* __restrict__ out_scale, unsigned char* __restrict__ out_zp,
+                                    int32_t* __restrict__ out_info, int only_if_partial) {
+  const unsigned int or_mask = *or_mask_p;
+  const int stop = mse_stop_index(or_mask);
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0 && out_info) { out_info[0] = stop; out_info[1] = (int32_t)or_mask; }
+  if (only_if_partial && or_mask == 0xFFFFFu) return;
+  if (r >= rows) return;
+  unsigned int mask = masks[r] & (stop >= 31 ? 0xFFFFFFFFu : ((2u << stop) - 1u));
+  // the running arg-min after step `stop` is the last step that improved; step 0 always improves
+  // (any finite error < FLT_MAX); if nothing improved (NaN/inf errors) the initial range is kept.
+  const int best_i = mask ? 31 - __clz(mask) : 0;
+  const float lo0 = fminf(ordered_to_float(enc_min[r]), 0.0f);
+  const float hi0 = fmaxf(ordered_to_float(enc_max[r]), 0.0f);
+  const float p = kShrink[best_i];
+  QParam qp = qparam_from_range(__fmul_rn(p, lo0), __fmul_rn(p, hi0), qs);
+  out_scale[r] = qp.scale;
+  out_zp[r] = encode_code(qp.zp, qs);
+}
+
+// A2 / A6 result as ranges: (min*clip, max*clip) with zero included, or the best shrunk range of
+// the MSE search (which starts from clip 1.0, utils.py:188).
+static __global__ void row_ranges_kernel(const unsigned int* __restrict__ enc_min,
+                                         const unsigned int* __restrict__ enc_max,
+                                         const unsigned int* __restrict__ masks,
+                                         const unsigned int* __restrict__ or_mask_p, int64_t rows,
+                                         float clip, float* __restrict__ out_min,
+                                         float* __restrict__ out_max) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float lo = ordered_to_float(enc_min[r]), hi = ordered_to_float(enc_max[r]);
+  if (!masks) {
+    out_min[r] = fminf(__fmul_rn(lo, clip), 0.0f);
+    out_max[r] = fmaxf(__fmul_rn(hi, clip), 0.0f);
+    return;
+  }
+  const int stop = mse_stop_index(*or_mask_p);
+  unsigned int mask = masks[r] & ((2u << stop) - 1u);
+  const float p = kShrink[mask ? 31 - __clz(mask) : 0];
+  out_min[r] = __fmul_rn(p, fminf(lo, 0.0f));
+  out_max[r] = __fmul_rn(p, fmaxf(hi, 0.0f));
+}
+
+}  // namespace b200q

@@ -1,0 +1,406 @@
+// rtn.cu — C-ABI entry points of the RTN / MSE / packing path (see include/b200q.h).
+#include "common.cuh"
+#include "minmax.cuh"
+#include "mse_generic.cuh"
+#include "rtn_fused.cuh"
+#include "rtn_generic.cuh"
+
+namespace b200q {
+
+// ---- small element-wise kernels -------------------------------------------------------------------
+__global__ void qparams_kernel(const float* __restrict__ rmin, const float* __restrict__ rmax,
+                               int64_t n, QSpec qs, float* __restrict__ out_scale,
+                               unsigned char* __restrict__ out_zp) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  QParam p = qparam_from_range(rmin[i], rmax[i], qs);
+  out_scale[i] = p.scale;
+  out_zp[i] = encode_code(p.zp, qs);
+}
+
+__global__ void dequantize_kernel(const unsigned char* __restrict__ codes, RowMap m, QSpec qs,
+                                  const float* __restrict__ scale,
+                                  const unsigned char* __restrict__ zp, float* __restrict__ out) {
+  int64_t total = m.K * m.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = i / m.N, n = i - k * m.N;
+    int64_t r = m.row_of(k, n);
+    int q = decode_code(codes[i], qs);
+    int z = decode_code(zp[r], qs);
+    out[i] = dequant_code(q, z, scale[r]);
+  }
+}
+
+__global__ void quantize_bias_kernel(const float* __restrict__ bias, int64_t n,
+                                     const float* __restrict__ wscale, int64_t n_wscale,
+                                     float input_scale, int32_t* __restrict__ out_q,
+                                     float* __restrict__ out_scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_wscale) out_scale[i] = __fmul_rn(wscale[i], input_scale);
+  if (i >= n) return;
+  // rtn.py:129-137: scale = weight_scale * input_scale; q = clip(int32(rint(b / scale)) + 0)
+  float s = __fmul_rn(wscale[n_wscale == 1 ? 0 : i], input_scale);
+  out_q[i] = __float2int_rn(__fdiv_rn(bias[i], s));
+}
+
+// ---- workspace carving ----------------------------------------------------------------------------
+struct RtnWorkspace {
+  unsigned int* or_mask;
+  unsigned int* enc_min;
+  unsigned int* enc_max;
+  unsigned int* masks;
+  unsigned char* zp_rows;
+  float2* partials;
+  float* err;
+  unsigned char* codes_tmp;
+  size_t total;
+};
+
+static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool mse) {
+  RtnWorkspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((char*)base + off) : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  w.or_mask = (unsigned int*)take(256);
+  w.enc_min = (unsigned int*)take((size_t)rows * 4);
+  w.enc_max = (unsigned int*)take((size_t)rows * 4);
+  w.masks = (unsigned int*)take((size_t)rows * 4);
+  w.zp_rows = (unsigned char*)take((size_t)rows);
+  w.partials = (float2*)take((size_t)kMinMaxMaxBlocks * sizeof(float2));
+  w.err = (float*)take(mse ? (size_t)rows * kMseCandidates * 4 : 0);
+  w.codes_tmp = (unsigned char*)take((size_t)K * N);
+  w.total = off;
+  return w;
+}
+
+struct Shape {
+  RowMap map;
+  int64_t rows;
+};
+
+static int resolve_shape(int64_t K, int64_t N, int strategy, int64_t group_size, Shape* s) {
+  B200Q_REQUIRE(K > 0 && N > 0, B200Q_ERR_INVALID_ARG, "K and N must be positive (K=%lld N=%lld)",
+                (long long)K, (long long)N);
+  RowMap m;
+  m.K = K; m.N = N; m.strategy = strategy;
+  if (strategy == B200Q_TENSOR) { m.gs = K; m.G = 1; }
+  else if (strategy == B200Q_CHANNEL) { m.gs = K; m.G = 1; }
+  else if (strategy == B200Q_GROUP) {
+    int64_t gs = (group_size == -1 || group_size > K) ? K : group_size;   // utils.py:19-22
+    B200Q_REQUIRE(gs > 0 && K % gs == 0, B200Q_ERR_INVALID_ARG,
+                  "group_size %lld does not divide K=%lld", (long long)group_size, (long long)K);
+    m.gs = gs; m.G = K / gs;
+  } else {
+    B200Q_REQUIRE(false, B200Q_ERR_INVALID_ARG, "unknown strategy %d", strategy);
+  }
+  s->map = m;
+  s->rows = m.rows();
+  return B200Q_OK;
+}
+
+static int elementwise_grid(int64_t total) {
+  int64_t b = ceil_div(total, 256);
+  if (b > kNumSMs * 16) b = kNumSMs * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// min/max of every parameter row -> enc_min / enc_max
+static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWorkspace& ws,
+                           cudaStream_t st) {
+  if (m.strategy == B200Q_TENSOR) {
+    int g = minmax_grid(m.K * m.N);
+    minmax_partials_kernel<<<g, kMinMaxThreads, 0, st>>>(W, m.K * m.N, ws.partials);
+    minmax_fold_kernel<<<1, kMinMaxThreads, 0, st>>>(ws.partials, g, nullptr, ws.enc_min, ws.enc_max);
+  } else {
+    B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_min, 0xFF, (size_t)rows * 4, st));
+    B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_max, 0x00, (size_t)rows * 4, st));
+    dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)ceil_div(m.K, kStatRowsPerCta));
+    rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, ws.enc_min, ws.enc_max, nullptr);
+  }
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+template <int GS>
+static void launch_fused(const FusedArgs& a, bool mse, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(a.N, kFusedCols), (unsigned)a.G);
+  if (mse) rtn_group_fused_kernel<GS, true><<<grid, 256, 0, st>>>(a);
+  else rtn_group_fused_kernel<GS, false><<<grid, 256, 0, st>>>(a);
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+size_t b200q_rtn_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t group_size, int mse) {
+  Shape s;
+  if (resolve_shape(K, N, strategy, group_size, &s) != B200Q_OK) return 0;
+  return carve(nullptr, s.rows, K, N, mse != 0).total;
+}
+
+int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                       int64_t group_size, int symmetric, int reduce_range, double clip_ratio,
+                       int mse, int layout, void* out_codes, float* out_scale, void* out_zp,
+                       int32_t* out_mse_info, void* workspace, size_t workspace_bytes,
+                       b200q_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200Q_REQUIRE(W && out_codes && out_scale && out_zp, B200Q_ERR_INVALID_ARG, "null pointer argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, symmetric, reduce_range, &qs), B200Q_ERR_INVALID_ARG,
+                "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  const RowMap& m = s.map;
+  B200Q_REQUIRE(layout == B200Q_KN_BYTES || layout == B200Q_PACKED_FLAT || layout == B200Q_MATMUL_NBITS,
+                B200Q_ERR_INVALID_ARG, "unknown layout %d", layout);
+  B200Q_REQUIRE(layout != B200Q_PACKED_FLAT || qs.bits == 4, B200Q_ERR_INVALID_ARG,
+                "PACKED_FLAT is the 4-bit initializer layout");
+  if (layout == B200Q_MATMUL_NBITS) {
+    // qrules/_common.py:32-62
+    B200Q_REQUIRE(strategy == B200Q_GROUP && !qs.is_signed, B200Q_ERR_INVALID_ARG,
+                  "MATMUL_NBITS needs uint4/uint8 and the group strategy");
+    B200Q_REQUIRE(m.gs >= 16 && (m.gs & (m.gs - 1)) == 0, B200Q_ERR_INVALID_ARG,
+                  "MATMUL_NBITS needs a power-of-two group size >= 16 (got %lld)", (long long)m.gs);
+  }
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0);
+  B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
+                "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
+  B200Q_REQUIRE(clip_ratio > 0.0 && clip_ratio <= 1.0, B200Q_ERR_INVALID_ARG,
+                "clip_ratio must be in (0, 1]");
+  const float clip = (float)clip_ratio;
+  unsigned char* zp_rows = layout == B200Q_MATMUL_NBITS ? ws.zp_rows : (unsigned char*)out_zp;
+  unsigned char* kn_dst = layout == B200Q_KN_BYTES ? (unsigned char*)out_codes : ws.codes_tmp;
+  const unsigned int* skip = nullptr;   // set on the fused-MSE route: skip fix-up when no early stop
+
+  const bool fused = strategy == B200Q_GROUP &&
+                     (m.gs == 16 || m.gs == 32 || m.gs == 64 || m.gs == 128) && N % 16 == 0 &&
+                     ((uintptr_t)W % 16 == 0) && ((uintptr_t)out_codes % 16 == 0);
+  if (mse) B200Q_CUDA_OK(cudaMemsetAsync(ws.or_mask, 0, 4, st));
+
+  if (fused) {
+    FusedArgs a;
+    a.W = W; a.K = K; a.N = N; a.G = m.G; a.qs = qs; a.clip = clip; a.layout = layout;
+    a.out_codes = (unsigned char*)out_codes; a.out_scale = out_scale; a.zp_rows = zp_rows;
+    a.masks = ws.masks; a.or_mask = ws.or_mask;
+    a.enc_min = ws.enc_min; a.enc_max = ws.enc_max;
+    switch (m.gs) {
+      case 16: launch_fused<16>(a, mse != 0, st); break;
+      case 32: launch_fused<32>(a, mse != 0, st); break;
+      case 64: launch_fused<64>(a, mse != 0, st); break;
+      default: launch_fused<128>(a, mse != 0, st); break;
+    }
+    B200Q_LAUNCH_OK();
+    if (mse) {
+      // The fused kernel assumed "no global early stop" (every step improved some row).  If the
+      // OR-mask says otherwise, redo the row decisions for the stop index and requantize; all of
+      // the fix-up kernels return immediately when the mask is full.
+      int blocks = (int)ceil_div(s.rows, 256);
+      mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.or_mask, ws.enc_min, ws.enc_max,
+                                                  s.rows, qs, out_scale, zp_rows, out_mse_info, 1);
+      B200Q_LAUNCH_OK();
+      skip = ws.or_mask;
+    }
+  } else {
+    rc = launch_rowstats(W, m, s.rows, ws, st);
+    if (rc != B200Q_OK) return rc;
+    int blocks = (int)ceil_div(s.rows, 256);
+    if (mse) {
+      const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
+      dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)m.G);
+      dim3 block(32, kMseCandidates);
+      mse_error_table_kernel<<<grid, block, 0, st>>>(W, m, qs, ws.enc_min, ws.enc_max, ws.err, nullptr);
+      B200Q_LAUNCH_OK();
+      mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.or_mask, nullptr);
+      B200Q_LAUNCH_OK();
+      mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.or_mask, ws.enc_min, ws.enc_max,
+                                                  s.rows, qs, out_scale, zp_rows, out_mse_info, 0);
+    } else {
+      qparams_from_stats_kernel<<<blocks, 256, 0, st>>>(ws.enc_min, ws.enc_max, s.rows, clip, qs,
+                                                        out_scale, zp_rows);
+    }
+    B200Q_LAUNCH_OK();
+  }
+
+  if (!fused || mse) {
+    // generic quantize (+ pack): the only route when !fused, the conditional fix-up when fused
+    quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, st>>>(W, m, qs, out_scale, zp_rows,
+                                                                  kn_dst, skip);
+    B200Q_LAUNCH_OK();
+    if (layout == B200Q_PACKED_FLAT) {
+      pack4_flat_kernel<<<elementwise_grid((K * N + 1) / 2), 256, 0, st>>>(
+          kn_dst, K * N, (unsigned char*)out_codes, skip);
+      B200Q_LAUNCH_OK();
+    } else if (layout == B200Q_MATMUL_NBITS) {
+      dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 128));
+      pack_matmul_nbits_kernel<<<grid, 256, 0, st>>>(kn_dst, K, N, qs.bits,
+                                                     (unsigned char*)out_codes, skip);
+      B200Q_LAUNCH_OK();
+    }
+  }
+  if (layout == B200Q_MATMUL_NBITS) {
+    pack_zp_matmul_nbits_kernel<<<elementwise_grid(s.rows), 256, 0, st>>>(
+        zp_rows, N, m.G, qs.bits, (unsigned char*)out_zp, nullptr);
+    B200Q_LAUNCH_OK();
+  }
+  return B200Q_OK;
+}
+
+int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                          int64_t group_size, int symmetric, int reduce_range, float* out_err,
+                          void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200Q_REQUIRE(W && out_err, B200Q_ERR_INVALID_ARG, "null pointer argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, symmetric, reduce_range, &qs), B200Q_ERR_INVALID_ARG,
+                "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, true);
+  B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
+                "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
+  rc = launch_rowstats(W, s.map, s.rows, ws, st);
+  if (rc != B200Q_OK) return rc;
+  const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
+  dim3 block(32, kMseCandidates);
+  mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, out_err, nullptr);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                     int64_t group_size, int symmetric, int reduce_range, double clip_ratio, int mse,
+                     float* out_min, float* out_max, void* workspace, size_t workspace_bytes,
+                     b200q_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200Q_REQUIRE(W && out_min && out_max, B200Q_ERR_INVALID_ARG, "null pointer argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, symmetric, reduce_range, &qs), B200Q_ERR_INVALID_ARG,
+                "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0);
+  B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
+                "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
+  rc = launch_rowstats(W, s.map, s.rows, ws, st);
+  if (rc != B200Q_OK) return rc;
+  int blocks = (int)ceil_div(s.rows, 256);
+  if (mse) {
+    B200Q_CUDA_OK(cudaMemsetAsync(ws.or_mask, 0, 4, st));
+    const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
+    dim3 block(32, kMseCandidates);
+    mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, ws.err, nullptr);
+    B200Q_LAUNCH_OK();
+    mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.or_mask, nullptr);
+    B200Q_LAUNCH_OK();
+  }
+  row_ranges_kernel<<<blocks, 256, 0, st>>>(ws.enc_min, ws.enc_max, mse ? ws.masks : nullptr,
+                                            ws.or_mask, s.rows, (float)clip_ratio, out_min, out_max);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_quantize_with_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy,
+                                int64_t group_size, int symmetric, int reduce_range,
+                                const float* scale, const void* zp, void* out_codes,
+                                b200q_stream_t stream) {
+  B200Q_REQUIRE(W && scale && zp && out_codes, B200Q_ERR_INVALID_ARG, "null pointer argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, symmetric, reduce_range, &qs), B200Q_ERR_INVALID_ARG,
+                "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
+      W, s.map, qs, scale, (const unsigned char*)zp, (unsigned char*)out_codes, nullptr);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_qparams(const float* rmin, const float* rmax, int64_t n, int qtype, int symmetric,
+                  int reduce_range, float* out_scale, void* out_zp, b200q_stream_t stream) {
+  B200Q_REQUIRE(rmin && rmax && out_scale && out_zp && n > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, symmetric, reduce_range, &qs), B200Q_ERR_INVALID_ARG,
+                "unknown quantization type %d", qtype);
+  qparams_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      rmin, rmax, n, qs, out_scale, (unsigned char*)out_zp);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_dequantize(const void* codes, int64_t K, int64_t N, int qtype, int strategy,
+                     int64_t group_size, const float* scale, const void* zp, float* out,
+                     b200q_stream_t stream) {
+  B200Q_REQUIRE(codes && scale && zp && out, B200Q_ERR_INVALID_ARG, "null pointer argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, 0, 0, &qs), B200Q_ERR_INVALID_ARG, "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  dequantize_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned char*)codes, s.map, qs, scale, (const unsigned char*)zp, out);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_quantize_bias(const float* bias, int64_t n, const float* weight_scale,
+                        int64_t n_weight_scale, float input_scale, int32_t* out_q,
+                        float* out_scale, b200q_stream_t stream) {
+  B200Q_REQUIRE(bias && weight_scale && out_q && out_scale && n > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  B200Q_REQUIRE(n_weight_scale == 1 || n_weight_scale == n, B200Q_ERR_INVALID_ARG,
+                "weight_scale must have 1 or n entries");   // rtn.py:127
+  quantize_bias_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      bias, n, weight_scale, n_weight_scale, input_scale, out_q, out_scale);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_pack4_flat(const void* codes, int64_t n_elements, void* out, b200q_stream_t stream) {
+  B200Q_REQUIRE(codes && out && n_elements > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  pack4_flat_kernel<<<elementwise_grid((n_elements + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned char*)codes, n_elements, (unsigned char*)out, nullptr);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_unpack4_flat(const void* packed, int64_t n_elements, void* out_codes,
+                       b200q_stream_t stream) {
+  B200Q_REQUIRE(packed && out_codes && n_elements > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  unpack4_flat_kernel<<<elementwise_grid(n_elements), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned char*)packed, n_elements, (unsigned char*)out_codes);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_pack_matmul_nbits(const void* codes, int64_t K, int64_t N, int64_t group_size, int bits,
+                            const void* zp_rows, void* out_B, void* out_zp, b200q_stream_t stream) {
+  B200Q_REQUIRE(codes && out_B && (bits == 4 || bits == 8), B200Q_ERR_INVALID_ARG, "bad argument");
+  B200Q_REQUIRE(group_size > 0 && K % group_size == 0, B200Q_ERR_INVALID_ARG,
+                "group_size must divide K");          // qrules/_common.py:72
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 128));
+  pack_matmul_nbits_kernel<<<grid, 256, 0, st>>>((const unsigned char*)codes, K, N, bits,
+                                                 (unsigned char*)out_B, nullptr);
+  B200Q_LAUNCH_OK();
+  if (zp_rows && out_zp) {
+    int64_t G = K / group_size;
+    pack_zp_matmul_nbits_kernel<<<elementwise_grid(N * G), 256, 0, st>>>(
+        (const unsigned char*)zp_rows, N, G, bits, (unsigned char*)out_zp, nullptr);
+    B200Q_LAUNCH_OK();
+  }
+  return B200Q_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// rtn_generic.cuh — shape-agnostic kernels of the RTN path (any group size, CHANNEL, TENSOR,
+// ragged N).  They are the exact but un-tuned route; the tuned single-pass kernels for the
+// benchmark shapes live in rtn_fused.cuh.  Parameter rows ("rows" below) are what the reference
+// obtains from `_preprocess_array` (utils.py:6-26):
+//     TENSOR  : 1 row, all K*N elements
+//     CHANNEL : N rows, row n = W[:, n]
+//     GROUP   : N*G rows (G = K/gs), row n*G+g = W[g*gs:(g+1)*gs, n]
+#pragma once
+
+#include "common.cuh"
+
+namespace b200q {
+
+struct RowMap {
+  int64_t K, N;
+  int64_t gs;   // rows of W per parameter row (K for CHANNEL, K*… unused for TENSOR)
+  int64_t G;    // groups per column (1 for CHANNEL)
+  int strategy;
+  __host__ __device__ int64_t rows() const { return strategy == B200Q_TENSOR ? 1 : N * G; }
+  __device__ __forceinline__ int64_t row_of(int64_t k, int64_t n) const {
+    return strategy == B200Q_TENSOR ? 0 : n * G + k / gs;
+  }
+};
+
+// ---- min/max per parameter row, column-segment strategies ---------------------------------
+// grid = (ceil(N/128), ceil(K/kRowsPerCta)); one thread per column walks its K-chunk and folds
+// into the order-preserving encoded min/max with one atomic pair per (column, group-in-chunk).
+constexpr int kStatRowsPerCta = 256;
+
+static __global__ void __launch_bounds__(128) rowstats_cols_kernel(const float* __restrict__ W, RowMap m,
+                                                            unsigned int* __restrict__ enc_min,
+                                                            unsigned int* __restrict__ enc_max,
+                                                            const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (n >= m.N) return;
+  int64_t k0 = (int64_t)blockIdx.y * kStatRowsPerCta;
+  int64_t k1 = min(k0 + (int64_t)kStatRowsPerCta, m.K);
+  float mn = INFINITY, mx = -INFINITY;
+  int64_t g = k0 / m.gs;
+  for (int64_t k = k0; k < k1; ++k) {
+    int64_t gk = k / m.gs;
+    if (gk != g) {
+      atomicMin(&enc_min[n * m.G + g], float_to_ordered(mn));
+      atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
+      mn = INFINITY; mx = -INFINITY; g = gk;
+    }
+    float v = __ldg(&W[k * m.N + n]);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  atomicMin(&enc_min[n * m.G + g], float_to_ordered(mn));
+  atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
+}
+
+// ---- encoded min/max -> (scale, zp) per row: A2 tail (clip, include zero) + A3 -----------------
+static __global__ void qparams_from_stats_kernel(const unsigned int* __restrict__ enc_min,
+                                          const unsigned int* __restrict__ enc_max, int64_t rows,
+                                          float clip, QSpec qs, float* __restrict__ out_scale,
+                                          unsigned char* __restrict__ out_zp) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  // utils.py:62-67: (min * clip_ratio) in f32, then include zero
+  float mn = fminf(__fmul_rn(ordered_to_float(enc_min[r]), clip), 0.0f);
+  float mx = fmaxf(__fmul_rn(ordered_to_float(enc_max[r]), clip), 0.0f);
+  QParam p = qparam_from_range(mn, mx, qs);
+  out_scale[r] = p.scale;
+  out_zp[r] = encode_code(p.zp, qs);
+}
+
+// ---- A4 with given per-row parameters, KN_BYTES output ------------------------------------------
+static __global__ void __launch_bounds__(256) quantize_rows_kernel(
+    const float* __restrict__ W, RowMap m, QSpec qs, const float* __restrict__ scale,
+    const unsigned char* __restrict__ zp, unsigned char* __restrict__ out,
+    const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  int64_t total = m.K * m.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = i / m.N, n = i - k * m.N;
+    int64_t r = m.row_of(k, n);
+    int z = decode_code(zp[r], qs);
+    int q = quant_code(__ldg(&W[i]), scale[r], z, qs.qmin, qs.qmax);
+    out[i] = encode_code(q, qs);
+  }
+}
+
+// ---- P1: flat nibble packing (core/_pack.py:8-22) -------------------------------------------------
+static __global__ void pack4_flat_kernel(const unsigned char* __restrict__ codes, int64_t n_elements,
+                                  unsigned char* __restrict__ out, const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  int64_t nbytes = (n_elements + 1) / 2;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nbytes;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    unsigned int lo = codes[2 * j] & 0xFu;
+    unsigned int hi = (2 * j + 1 < n_elements) ? (codes[2 * j + 1] & 0xFu) : 0u;
+    out[j] = (unsigned char)(lo | (hi << 4));
+  }
+}
+
+static __global__ void unpack4_flat_kernel(const unsigned char* __restrict__ packed,
+                                           int64_t n_elements, unsigned char* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elements;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned int b = packed[i >> 1];
+    out[i] = (unsigned char)((i & 1) ? (b >> 4) : (b & 0xFu));
+  }
+}
+
+// ---- P2: MatMulNBits weight blob (qrules/_common.py:76-87) ---------------------------------------
+// codes (K,N) bytes -> B (N, G, gs*bits/8).  A 32-column x 128-row tile is transposed through
+// shared memory so that both the read (along N) and the write (along K) are contiguous runs.
+static __global__ void __launch_bounds__(256) pack_matmul_nbits_kernel(
+    const unsigned char* __restrict__ codes, int64_t K, int64_t N, int bits,
+    unsigned char* __restrict__ out, const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  __shared__ unsigned char tile[32][132];
+  int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 128;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 128; r += 8) {
+    int64_t k = k0 + r, n = n0 + tx;
+    tile[tx][r] = (k < K && n < N) ? codes[k * N + n] : 0;
+  }
+  __syncthreads();
+  // per column: 128 codes -> 64 (4-bit) or 128 (8-bit) output bytes, contiguous in `out`
+  int out_per_col = bits == 4 ? 64 : 128;
+  int64_t col_stride = K * bits / 8;     // bytes per output channel in B (G * gs*bits/8)
+  int64_t b0 = k0 * bits / 8;
+  for (int idx = threadIdx.x; idx < 32 * out_per_col; idx += 256) {
+    int c = idx / out_per_col, j = idx - c * out_per_col;
+    int64_t n = n0 + c;
+    if (n >= N) continue;
+    unsigned char v;
+    if (bits == 4) {
+      if (k0 + 2 * j >= K) continue;
+      v = (unsigned char)((tile[c][2 * j] & 0xF) | ((tile[c][2 * j + 1] & 0xF) << 4));
+    } else {
+      if (k0 + j >= K) continue;
+      v = tile[c][j];
+    }
+    out[n * col_stride + b0 + j] = v;
+  }
+}
+
+// zero points of MatMulNBits (qrules/_common.py:96-121): (N, G) bytes -> (N, ceil(G/2)) nibbles,
+// low nibble = even g, odd count padded with 0x8.  G == 1 or 8-bit: plain copy.
+static __global__ void pack_zp_matmul_nbits_kernel(const unsigned char* __restrict__ zp_rows, int64_t N,
+                                            int64_t G, int bits, unsigned char* __restrict__ out,
+                                            const unsigned int* skip_if_full) {
+  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+  bool packed = bits == 4 && G > 1;
+  int64_t per_row = packed ? (G + 1) / 2 : G;
+  int64_t total = N * per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!packed) { out[i] = zp_rows[i]; continue; }
+    int64_t n = i / per_row, j = i - n * per_row;
+    unsigned int lo = zp_rows[n * G + 2 * j] & 0xFu;
+    unsigned int hi = (2 * j + 1 < G) ? (zp_rows[n * G + 2 * j + 1] & 0xFu) : 0x8u;
+    out[i] = (unsigned char)(lo | (hi << 4));
+  }
+}
+
+}  // namespace b200q
