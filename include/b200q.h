@@ -68,6 +68,7 @@ enum b200q_gptq_mode { B200Q_GPTQ_REFERENCE = 0, B200Q_GPTQ_PROPAGATE = 1 };
 int b200q_version(void);
 const char* b200q_status_string(int status);
 const char* b200q_last_error(void); /* thread-local text of the last failing call */
+long long b200q_launch_count(void); /* kernels this library has launched in this process */
 
 /* ---------------------------------------------------------------------------------------------
  * RTN weight quantization — replaces `_rtn_quantize` (core/_algorithms/rtn.py:54-109), i.e.

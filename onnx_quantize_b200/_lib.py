@@ -37,6 +37,7 @@ _SIGNATURES = {
     "b200q_version": (ctypes.c_int, []),
     "b200q_status_string": (ctypes.c_char_p, [_i32]),
     "b200q_last_error": (ctypes.c_char_p, []),
+    "b200q_launch_count": (ctypes.c_longlong, []),
     "b200q_rtn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32]),
     "b200q_rtn_quantize": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _i32,
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),

@@ -1,5 +1,7 @@
 // api.cu — version / status / error text, and host-side q-range resolution.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,6 +9,9 @@
 namespace b200q {
 
 static thread_local char g_last_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -74,5 +79,7 @@ const char* b200q_status_string(int status) {
 }
 
 const char* b200q_last_error(void) { return b200q::g_last_error; }
+
+long long b200q_launch_count(void) { return b200q::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

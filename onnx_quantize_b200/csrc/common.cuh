@@ -18,6 +18,7 @@
 namespace b200q {
 
 void set_last_error(const char* fmt, ...);
+void count_launch();   // bumps the process-wide kernel-launch counter (b200q_launch_count)
 
 #define B200Q_REQUIRE(cond, code, ...)          \
   do {                                          \
@@ -40,6 +41,7 @@ void set_last_error(const char* fmt, ...);
 #define B200Q_LAUNCH_OK()                                                                \
   do {                                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \
+    ::b200q::count_launch();                                                             \
     if (e__ != cudaSuccess) {                                                            \
       ::b200q::set_last_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
                               __FILE__, __LINE__);                                       \

@@ -28,32 +28,55 @@ struct ErrFn {
   }
 };
 
-// numpy/_core/src/umath/loops_utils.h.src::pairwise_sum (PW_BLOCKSIZE 128, unroll 8)
+// numpy/_core/src/umath/loops_utils.h.src::pairwise_sum (PW_BLOCKSIZE 128, unroll 8).
+// Leaf: n <= 128 elements starting at `off`.
 template <class F>
-__device__ float pairwise_sum(const F& f, int64_t off, int64_t n) {
+__device__ __forceinline__ float pairwise_leaf(const F& f, int64_t off, int64_t n) {
   if (n < 8) {
     float res = -0.0f;
     for (int64_t i = 0; i < n; ++i) res = __fadd_rn(res, f(off + i));
     return res;
-  } else if (n <= 128) {
-    float r[8];
+  }
+  float r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = f(off + j);
-    int64_t i;
-    for (i = 8; i < n - (n % 8); i += 8) {
+  for (int j = 0; j < 8; ++j) r[j] = f(off + j);
+  int64_t i;
+  for (i = 8; i < n - (n % 8); i += 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], f(off + i + j));
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], f(off + i + j));
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, f(off + i));
+  return res;
+}
+
+// The recursion `P(a, n) = P(a, n2) + P(a + n2, n - n2)`, n2 = n/2 - (n/2)%8, unrolled into an
+// explicit stack (one frame per level, <= 64 levels for any int64 n) — device recursion would
+// need a call stack sized for the deepest tensor.
+template <class F>
+__device__ float pairwise_sum(const F& f, int64_t off, int64_t n) {
+  struct Frame { int64_t off, n; float left; int have_left; };
+  Frame st[64];
+  int sp = 0;
+  for (;;) {
+    while (n > 128) {   // descend into the left half, remember the right half
+      int64_t n2 = n / 2;
+      n2 -= n2 % 8;
+      st[sp].off = off + n2; st[sp].n = n - n2; st[sp].have_left = 0; ++sp;
+      n = n2;
     }
-    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __fadd_rn(res, f(off + i));
-    return res;
-  } else {
-    int64_t n2 = n / 2;
-    n2 -= n2 % 8;
-    float a = pairwise_sum(f, off, n2);
-    float b = pairwise_sum(f, off + n2, n - n2);
-    return __fadd_rn(a, b);
+    float v = pairwise_leaf(f, off, n);
+    for (;;) {
+      if (sp == 0) return v;
+      Frame& top = st[sp - 1];
+      if (!top.have_left) {   // v is the left sum: now evaluate the right half
+        top.left = v; top.have_left = 1; off = top.off; n = top.n;
+        break;
+      }
+      v = __fadd_rn(top.left, v);   // v was the right sum
+      --sp;
+    }
   }
 }
 

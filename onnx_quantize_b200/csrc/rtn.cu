@@ -115,6 +115,7 @@ static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWor
   if (m.strategy == B200Q_TENSOR) {
     int g = minmax_grid(m.K * m.N);
     minmax_partials_kernel<<<g, kMinMaxThreads, 0, st>>>(W, m.K * m.N, ws.partials);
+    B200Q_LAUNCH_OK();
     minmax_fold_kernel<<<1, kMinMaxThreads, 0, st>>>(ws.partials, g, nullptr, ws.enc_min, ws.enc_max);
   } else {
     B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_min, 0xFF, (size_t)rows * 4, st));
