@@ -59,6 +59,12 @@ enum b200q_strategy { B200Q_TENSOR = 0, B200Q_CHANNEL = 1, B200Q_GROUP = 2 };
 enum b200q_layout { B200Q_KN_BYTES = 0, B200Q_PACKED_FLAT = 1, B200Q_MATMUL_NBITS = 2 };
 
 /* Hessian contraction precision on the tcgen05 tensor cores. */
+/* `mse` argument of the RTN entry points.  ON evaluates the shrink-grid search with the two-tier
+ * scheme (approximate scores prove most decisions, the exact float32 sequence settles the rest);
+ * EXACT evaluates every candidate with the exact sequence (verification / fallback).  Both give
+ * the reference's result. */
+enum b200q_mse_mode { B200Q_MSE_OFF = 0, B200Q_MSE_ON = 1, B200Q_MSE_EXACT = 2 };
+
 enum b200q_precision { B200Q_TF32 = 0, B200Q_TF32X3 = 1 };
 
 /* GPTQ update rule: REFERENCE reproduces gptq.py:198-208 as written (reads the zero triangle of
@@ -103,6 +109,10 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
 int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int strategy,
                           int64_t group_size, int symmetric, int reduce_range, float* out_err,
                           void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/* Diagnostic: the approximate |x|**2.4 (MUFU lg2/ex2) used by the first tier of the MSE search,
+ * element-wise; tests measure its error bound on the device. */
+int b200q_debug_pow_approx(const float* x, int64_t n, float* out, b200q_stream_t stream);
 
 /* Quantization range per parameter row — replaces `_compute_min_max` (utils.py:42-69) and, with
  * mse != 0, `_compute_min_max_mse` (utils.py:140-239).  out_min/out_max hold one f32 per row

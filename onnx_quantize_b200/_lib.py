@@ -43,6 +43,7 @@ _SIGNATURES = {
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "b200q_mse_error_table": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _ptr, _ptr,
                                       _sz, _ptr]),
+    "b200q_debug_pow_approx": (_i32, [_ptr, _i64, _ptr, _ptr]),
     "b200q_row_ranges": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _ptr,
                                  _ptr, _ptr, _sz, _ptr]),
     "b200q_quantize_with_qparams": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _ptr,

@@ -128,10 +128,26 @@ static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWor
 }
 
 template <int GS>
-static void launch_fused(const FusedArgs& a, bool mse, cudaStream_t st) {
+static void launch_fused(const FusedArgs& a, int mode, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(a.N, kFusedCols), (unsigned)a.G);
-  if (mse) rtn_group_fused_kernel<GS, true><<<grid, 256, 0, st>>>(a);
-  else rtn_group_fused_kernel<GS, false><<<grid, 256, 0, st>>>(a);
+  if (mode == kTwoTier) rtn_group_fused_kernel<GS, kTwoTier><<<grid, kFusedThreads, 0, st>>>(a);
+  else if (mode == kExact) rtn_group_fused_kernel<GS, kExact><<<grid, kFusedThreads, 0, st>>>(a);
+  else rtn_group_fused_kernel<GS, kPlain><<<grid, kFusedThreads, 0, st>>>(a);
+}
+
+static void launch_fused_gs(const FusedArgs& a, int64_t gs, int mode, cudaStream_t st) {
+  switch (gs) {
+    case 16: launch_fused<16>(a, mode, st); break;
+    case 32: launch_fused<32>(a, mode, st); break;
+    case 64: launch_fused<64>(a, mode, st); break;
+    default: launch_fused<128>(a, mode, st); break;
+  }
+}
+
+__global__ void pow_approx_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = pow_norm_approx(fabsf(x[i]));
 }
 
 }  // namespace b200q
@@ -184,7 +200,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
   const bool fused = strategy == B200Q_GROUP &&
                      (m.gs == 16 || m.gs == 32 || m.gs == 64 || m.gs == 128) && N % 16 == 0 &&
                      ((uintptr_t)W % 16 == 0) && ((uintptr_t)out_codes % 16 == 0);
-  if (mse) B200Q_CUDA_OK(cudaMemsetAsync(ws.or_mask, 0, 4, st));
+  if (mse) B200Q_CUDA_OK(cudaMemsetAsync(ws.or_mask, 0, 8, st));   // or_mask and proven-mask
 
   if (fused) {
     FusedArgs a;
@@ -192,13 +208,23 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     a.out_codes = (unsigned char*)out_codes; a.out_scale = out_scale; a.zp_rows = zp_rows;
     a.masks = ws.masks; a.or_mask = ws.or_mask;
     a.enc_min = ws.enc_min; a.enc_max = ws.enc_max;
-    switch (m.gs) {
-      case 16: launch_fused<16>(a, mse != 0, st); break;
-      case 32: launch_fused<32>(a, mse != 0, st); break;
-      case 64: launch_fused<64>(a, mse != 0, st); break;
-      default: launch_fused<128>(a, mse != 0, st); break;
+    a.run_unless_full = nullptr; a.set_full_when_skipped = nullptr;
+    if (!mse) {
+      launch_fused_gs(a, m.gs, kPlain, st);
+      B200Q_LAUNCH_OK();
+    } else {
+      if (mse != B200Q_MSE_EXACT) {
+        // tier 1+2 in one kernel; its OR of *proven* improvements goes to ws.or_mask[1]
+        FusedArgs t = a;
+        t.or_mask = ws.or_mask + 1;
+        launch_fused_gs(t, m.gs, kTwoTier, st);
+        B200Q_LAUNCH_OK();
+        a.run_unless_full = ws.or_mask + 1;       // exact kernel only if "no early stop" is unproven
+        a.set_full_when_skipped = ws.or_mask;
+      }
+      launch_fused_gs(a, m.gs, kExact, st);
+      B200Q_LAUNCH_OK();
     }
-    B200Q_LAUNCH_OK();
     if (mse) {
       // The fused kernel assumed "no global early stop" (every step improved some row).  If the
       // OR-mask says otherwise, redo the row decisions for the stop index and requantize; all of
@@ -325,6 +351,13 @@ int b200q_quantize_with_qparams(const float* W, int64_t K, int64_t N, int qtype,
   if (rc != B200Q_OK) return rc;
   quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
       W, s.map, qs, scale, (const unsigned char*)zp, (unsigned char*)out_codes, nullptr);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_debug_pow_approx(const float* x, int64_t n, float* out, b200q_stream_t stream) {
+  B200Q_REQUIRE(x && out && n > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  pow_approx_kernel<<<elementwise_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, out);
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }

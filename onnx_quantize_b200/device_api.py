@@ -36,6 +36,13 @@ def _strategy(strategy) -> int:
     return _lib.STRATEGY[name]
 
 
+def _mse_mode(mse) -> int:
+    """False → 0, True → 1 (two-tier search), "exact" → 2 (every candidate exactly)."""
+    if isinstance(mse, str):
+        return {"off": 0, "on": 1, "exact": 2}[mse]
+    return int(bool(mse))
+
+
 def _check_weight(w: torch.Tensor) -> tuple[int, int]:
     if not (isinstance(w, torch.Tensor) and w.is_cuda and w.dtype == torch.float32
             and w.dim() == 2 and w.is_contiguous()):
@@ -91,11 +98,11 @@ def rtn_quantize(w: torch.Tensor, quant_type, strategy, group_size=-1, is_symmet
         zp = torch.empty((n, zp_cols), dtype=torch.uint8, device=device)
         scale = torch.empty((n, g), dtype=torch.float32, device=device)
     info = torch.zeros((2,), dtype=torch.int32, device=device) if (mse and return_info) else None
-    nbytes = lib.b200q_rtn_workspace_bytes(k, n, st, int(group_size or -1), int(bool(mse)))
+    nbytes = lib.b200q_rtn_workspace_bytes(k, n, st, int(group_size or -1), _mse_mode(mse))
     ws = dev.workspace(nbytes)
     rc = lib.b200q_rtn_quantize(w.data_ptr(), k, n, qt, st, int(group_size or -1),
                                 int(bool(is_symmetric)), int(bool(reduce_range)),
-                                float(clip_ratio), int(bool(mse)), lay, codes.data_ptr(),
+                                float(clip_ratio), _mse_mode(mse), lay, codes.data_ptr(),
                                 scale.data_ptr(), zp.data_ptr(), dev.ptr(info), ws.data_ptr(),
                                 ws.numel(), dev.stream_ptr())
     _lib.check(rc, "b200q_rtn_quantize")
@@ -189,6 +196,15 @@ def quantize_bias(bias: torch.Tensor, input_scale: float, weight_scale: torch.Te
                                  dev.stream_ptr())
     _lib.check(rc, "b200q_quantize_bias")
     return q, s
+
+
+def debug_pow_approx(x: torch.Tensor) -> torch.Tensor:
+    """|x| ** 2.4 as the first tier of the MSE search evaluates it (MUFU lg2 / ex2)."""
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    _lib.check(lib.b200q_debug_pow_approx(x.data_ptr(), x.numel(), out.data_ptr(), dev.stream_ptr()),
+               "b200q_debug_pow_approx")
+    return out
 
 
 def pack4_flat(codes: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,82 @@
+"""The two-tier MSE search: (1) the measured error bound of the approximate |d|^2.4 that its
+proof rests on, (2) identity of its results with the exact evaluation of every candidate at the
+benchmark's shapes (size-independent property: same codes, scales, zero points, packed bytes)."""
+import numpy as np
+import pytest
+import torch
+
+from onnx_quantize_b200 import device_api as D
+from oracle import np_oracle as O
+from tests.helpers import bits
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pow_approx_error_bound(cuda):
+    """delta budget of rtn_fused.cuh::kTierTau assumes <= 8e-6 relative error over the range of
+    residuals a quantization error can take (|d| from 1e-12 to 1e4)."""
+    g = torch.Generator(device=cuda)
+    g.manual_seed(0)
+    worst = 0.0
+    for lo, hi in ((-12, -6), (-6, -3), (-3, 0), (0, 4)):
+        e = torch.rand(8_000_000, device=cuda, generator=g, dtype=torch.float64) * (hi - lo) + lo
+        x = (10.0 ** e).to(torch.float32)
+        approx = D.debug_pow_approx(x).to(torch.float64)
+        exact = x.to(torch.float64) ** float(np.float32(2.4))
+        rel = ((approx - exact).abs() / exact).max().item()
+        worst = max(worst, rel)
+    assert worst < 8e-6, worst
+    z = D.debug_pow_approx(torch.zeros(4, device=cuda))
+    assert torch.all(z == 0)
+
+
+@pytest.mark.parametrize("qt,sym,gs,shape", [
+    ("uint4", False, 128, (4096, 4096)), ("uint4", False, 128, (14336, 1024)),
+    ("int4", True, 128, (2048, 4096)), ("uint4", True, 64, (1024, 2048)),
+    ("int8", False, 32, (1024, 1024)), ("uint8", False, 16, (512, 2048)), ("int4", False, 16, (512, 512)),
+])
+def test_two_tier_equals_exact(cuda, qt, sym, gs, shape):
+    g = torch.Generator(device=cuda)
+    g.manual_seed(hash((qt, gs, shape)) & 0xFFFF)
+    w = torch.randn(shape, device=cuda, generator=g) * 0.02
+    w.view(-1)[torch.randint(0, w.numel(), (2000,), device=cuda, generator=g)] *= 20
+    layout = "matmul_nbits" if qt.startswith("u") else ("packed_flat" if "4" in qt else "kn")
+    a = D.rtn_quantize(w, qt, "group", gs, sym, False, 1.0, True, layout=layout, return_info=True)
+    b = D.rtn_quantize(w, qt, "group", gs, sym, False, 1.0, "exact", layout=layout, return_info=True)
+    for ta, tb in zip(a[:3], b[:3]):
+        assert torch.equal(ta, tb)
+    assert a[3].tolist() == [19, 0xFFFFF] and b[3].tolist() == [19, 0xFFFFF]
+
+
+def test_two_tier_tiny_inputs_take_the_exact_route(cuda):
+    """With a single tile the 'some row improved' mask cannot be proven full: the fallback kernel
+    must reproduce the reference's early stop."""
+    rng = np.random.default_rng(1)
+    for k, n in ((16, 16), (32, 16), (128, 16), (64, 32)):
+        w = (rng.standard_normal((k, n)) * 0.1).astype(np.float32)
+        wt = torch.from_numpy(w).to(cuda)
+        q, s, z, info = D.rtn_quantize(wt, "uint4", "group", 16, False, False, 1.0, True, return_info=True)
+        qo, so, zo = O.rtn_quantize(w, "uint4", "group", 16, False, False, 1.0, True)
+        rows = O.to_rows(w, "group", 16)
+        _, _, trace = O.mse_min_max(rows, "uint4", "group", False, False, return_trace=True)
+        assert int(info[0]) == len(trace) - 1
+        assert np.array_equal(bits(s.cpu().numpy()), bits(so.reshape(-1)))
+        assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8))
+
+
+def test_two_tier_adversarial_ties(cuda):
+    """Groups engineered so that several candidates have (nearly) equal errors: constant groups,
+    two-valued groups, groups of exact grid points, all-zero groups."""
+    rng = np.random.default_rng(2)
+    k, n = 1024, 256
+    w = np.zeros((k, n), np.float32)
+    w[:, 0:64] = rng.choice([-1.0, 1.0], size=(k, 64)).astype(np.float32) * 0.5      # two-valued
+    w[:, 64:128] = (rng.integers(-7, 9, size=(k, 64)) * 0.125).astype(np.float32)    # grid points
+    w[:, 128:192] = 0.37                                                               # constant
+    w[:, 192:] = (rng.standard_normal((k, 64)) * 1e-20).astype(np.float32)           # underflowing errors
+    wt = torch.from_numpy(w).to(cuda)
+    for qt, sym in (("uint4", False), ("int4", True), ("int8", False)):
+        q, s, z = D.rtn_quantize(wt, qt, "group", 128, sym, False, 1.0, True)
+        qo, so, zo = O.rtn_quantize(w, qt, "group", 128, sym, False, 1.0, True)
+        assert np.array_equal(bits(s.cpu().numpy()), bits(so.reshape(-1))), qt
+        assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8)), qt
