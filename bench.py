@@ -177,11 +177,11 @@ def run_gpu_arm(args):
     in_bytes = 4 * elts
     qt = QuantType.QUInt4
 
+    plans = {mse: D.RtnBatchPlan(weights, qt, "group", 128, False, False, 0.9, mse, layout="matmul_nbits")
+             for mse in (False, True)}
+
     def step(mse: bool):
-        outs = None
-        for w in weights:
-            outs = D.rtn_quantize(w, qt, "group", 128, False, False, 0.9, mse, layout="matmul_nbits")
-        return outs
+        return plans[mse].run()
 
     def sync_all():
         if world > 1:

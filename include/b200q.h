@@ -104,6 +104,26 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
                        int32_t* out_mse_info, void* workspace, size_t workspace_bytes,
                        b200q_stream_t stream);
 
+/* Many weights with one configuration in one call (a whole model's linear layers).  Semantically
+ * a loop of b200q_rtn_quantize over `jobs`; the workspace is shared (sized for the largest job)
+ * and the launches are issued back to back from C, so the host cost per weight is a few
+ * microseconds instead of one foreign-function round trip. */
+typedef struct b200q_rtn_job {
+  const float* W;        /* (K,N) row-major f32, device */
+  int64_t K, N;
+  void* out_codes;       /* as b200q_rtn_quantize */
+  float* out_scale;
+  void* out_zp;
+  int32_t* out_mse_info; /* may be NULL */
+} b200q_rtn_job;
+
+size_t b200q_rtn_batch_workspace_bytes(const b200q_rtn_job* jobs, int64_t n_jobs, int strategy,
+                                       int64_t group_size, int mse);
+int b200q_rtn_quantize_batch(const b200q_rtn_job* jobs, int64_t n_jobs, int qtype, int strategy,
+                             int64_t group_size, int symmetric, int reduce_range,
+                             double clip_ratio, int mse, int layout, void* workspace,
+                             size_t workspace_bytes, b200q_stream_t stream);
+
 /* Per-candidate error sums of the MSE search (utils.py:197-224) for every parameter row:
  * out_err is f32 [20][rows].  Diagnostic/test entry point used to pin the summation order. */
 int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int strategy,

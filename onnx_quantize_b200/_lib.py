@@ -23,6 +23,14 @@ PRECISION = {"tf32": 0, "tf32x3": 1}
 GPTQ_MODE = {"reference": 0, "propagate": 1}
 
 
+class RtnJob(ctypes.Structure):
+    """struct b200q_rtn_job of include/b200q.h."""
+
+    _fields_ = [("W", ctypes.c_void_p), ("K", ctypes.c_int64), ("N", ctypes.c_int64),
+                ("out_codes", ctypes.c_void_p), ("out_scale", ctypes.c_void_p),
+                ("out_zp", ctypes.c_void_p), ("out_mse_info", ctypes.c_void_p)]
+
+
 class B200QuantError(RuntimeError):
     """A libb200quant call failed (CUDA error, workspace, unsupported configuration)."""
 
@@ -41,6 +49,9 @@ _SIGNATURES = {
     "b200q_rtn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32]),
     "b200q_rtn_quantize": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _i32,
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "b200q_rtn_batch_workspace_bytes": (_sz, [_ptr, _i64, _i32, _i64, _i32]),
+    "b200q_rtn_quantize_batch": (_i32, [_ptr, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _i32,
+                                         _ptr, _sz, _ptr]),
     "b200q_mse_error_table": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _ptr, _ptr,
                                       _sz, _ptr]),
     "b200q_debug_pow_approx": (_i32, [_ptr, _i64, _ptr, _ptr]),

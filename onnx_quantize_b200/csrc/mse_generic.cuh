@@ -91,9 +91,7 @@ __device__ float sequential_sum(const F& f, int64_t n) {
 // err is f32 [20][rows].
 static __global__ void __launch_bounds__(32 * kMseCandidates) mse_error_table_kernel(
     const float* __restrict__ W, RowMap m, QSpec qs, const unsigned int* __restrict__ enc_min,
-    const unsigned int* __restrict__ enc_max, float* __restrict__ err,
-    const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+    const unsigned int* __restrict__ enc_max, float* __restrict__ err) {
   const int cand = threadIdx.y;
   const bool tensor = m.strategy == B200Q_TENSOR;
   const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -123,10 +121,7 @@ static __global__ void __launch_bounds__(32 * kMseCandidates) mse_error_table_ke
 
 // Per row: the "improved at step i" mask of the strict-< running minimum (utils.py:225-231).
 static __global__ void mse_row_masks_kernel(const float* __restrict__ err, int64_t rows,
-                                     unsigned int* __restrict__ masks,
-                                     unsigned int* __restrict__ or_mask,
-                                     const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+                                            unsigned int* __restrict__ masks, MseControl* ctl) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int mask = 0;
   if (r < rows) {
@@ -138,34 +133,50 @@ static __global__ void mse_row_masks_kernel(const float* __restrict__ err, int64
     masks[r] = mask;
   }
   unsigned int any = __reduce_or_sync(0xffffffffu, mask);
-  if ((threadIdx.x & 31) == 0 && any) atomicOr(or_mask, any);
+  if ((threadIdx.x & 31) == 0 && any) atomicOr(&ctl->or_mask, any);
 }
 
-// Global early stop (utils.py:232-237): the counter is incremented at every step at which NO row
-// improved and is never reset; the loop ends after the step at which it reaches `patience`.
-__device__ __forceinline__ int mse_stop_index(unsigned int or_mask) {
-  int stalls = 0;
-  for (int i = 0; i < kMseCandidates; ++i) {
-    if (!((or_mask >> i) & 1u)) ++stalls;
-    if (stalls >= kMsePatience) return i;
-  }
-  return kMseCandidates - 1;
+// After the optimistic two-tier run: is the early-stop index determined by the evidence?
+// P = proven improvements, Q = improvements that cannot be ruled out, P <= true mask <= Q, and the
+// stop index is monotone in the mask, so stop(P) == stop(Q) pins it.
+static __global__ void mse_decide_kernel(MseControl* ctl) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int lo = mse_stop_index(ctl->proven_or), hi = mse_stop_index(ctl->possible_or);
+  if (lo != hi) { ctl->state = kMseNeedExact; return; }
+  ctl->stop = lo;
+  if (lo == kMseCandidates - 1) { ctl->state = kMseDone; return; }
+  ctl->n_cand = lo + 1;          // the search really ended after step `lo`: redo on that prefix
+  ctl->state = kMseRerun;
 }
+
+enum FinalizeMode { kFinalizeGeneric = 0, kFinalizeFused = 1, kFinalizeFusedForcedExact = 2 };
 
 // masks + global stop index -> best candidate per row -> (scale, zp).
-static __global__ void mse_finalize_kernel(const unsigned int* __restrict__ masks,
-                                    const unsigned int* __restrict__ or_mask_p,
-                                    const unsigned int* __restrict__ enc_min,
-                                    const unsigned int* __restrict__ enc_max, int64_t rows, QSpec qs,
-                                    float* __restrict__ out_scale, unsigned char* __restrict__ out_zp,
-                                    int32_t* __restrict__ out_info, int only_if_partial) {
-  const unsigned int or_mask = *or_mask_p;
+//   generic: always (this is where scale/zp are produced)
+//   fused:   only if the exact kernel ran AND the stop index cut the search short; otherwise the
+//            fused kernels' outputs are final and only `out_info` is written
+static __global__ void mse_finalize_kernel(const unsigned int* __restrict__ masks, MseControl* ctl,
+                                           const unsigned int* __restrict__ enc_min,
+                                           const unsigned int* __restrict__ enc_max, int64_t rows,
+                                           QSpec qs, float* __restrict__ out_scale,
+                                           unsigned char* __restrict__ out_zp,
+                                           int32_t* __restrict__ out_info, int mode) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int state = mode == kFinalizeFused ? ctl->state : kMseNeedExact;
+  if (state != kMseNeedExact) {
+    if (r == 0 && out_info) { out_info[0] = ctl->stop; out_info[1] = (int32_t)ctl->proven_or; }
+    return;
+  }
+  const unsigned int or_mask = ctl->or_mask;
   const int stop = mse_stop_index(or_mask);
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r == 0 && out_info) { out_info[0] = stop; out_info[1] = (int32_t)or_mask; }
-  if (only_if_partial && or_mask == 0xFFFFFu) return;
+  if (r == 0) {
+    ctl->state = kMseNeedExact;
+    ctl->stop = stop;
+    if (out_info) { out_info[0] = stop; out_info[1] = (int32_t)or_mask; }
+  }
+  if (mode != kFinalizeGeneric && stop == kMseCandidates - 1) return;
   if (r >= rows) return;
-  unsigned int mask = masks[r] & (stop >= 31 ? 0xFFFFFFFFu : ((2u << stop) - 1u));
+  unsigned int mask = masks[r] & ((2u << stop) - 1u);
   // the running arg-min after step `stop` is the last step that improved; step 0 always improves
   // (any finite error < FLT_MAX); if nothing improved (NaN/inf errors) the initial range is kept.
   const int best_i = mask ? 31 - __clz(mask) : 0;
@@ -182,7 +193,7 @@ static __global__ void mse_finalize_kernel(const unsigned int* __restrict__ mask
 static __global__ void row_ranges_kernel(const unsigned int* __restrict__ enc_min,
                                          const unsigned int* __restrict__ enc_max,
                                          const unsigned int* __restrict__ masks,
-                                         const unsigned int* __restrict__ or_mask_p, int64_t rows,
+                                         const MseControl* ctl, int64_t rows,
                                          float clip, float* __restrict__ out_min,
                                          float* __restrict__ out_max) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +204,7 @@ static __global__ void row_ranges_kernel(const unsigned int* __restrict__ enc_mi
     out_max[r] = fmaxf(__fmul_rn(hi, clip), 0.0f);
     return;
   }
-  const int stop = mse_stop_index(*or_mask_p);
+  const int stop = mse_stop_index(ctl->or_mask);
   unsigned int mask = masks[r] & ((2u << stop) - 1u);
   const float p = kShrink[mask ? 31 - __clz(mask) : 0];
   out_min[r] = __fmul_rn(p, fminf(lo, 0.0f));

@@ -46,7 +46,7 @@ __global__ void quantize_bias_kernel(const float* __restrict__ bias, int64_t n,
 
 // ---- workspace carving ----------------------------------------------------------------------------
 struct RtnWorkspace {
-  unsigned int* or_mask;
+  MseControl* ctl;
   unsigned int* enc_min;
   unsigned int* enc_max;
   unsigned int* masks;
@@ -65,7 +65,7 @@ static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool m
     off += align_up(bytes, 256);
     return p;
   };
-  w.or_mask = (unsigned int*)take(256);
+  w.ctl = (MseControl*)take(256);
   w.enc_min = (unsigned int*)take((size_t)rows * 4);
   w.enc_max = (unsigned int*)take((size_t)rows * 4);
   w.masks = (unsigned int*)take((size_t)rows * 4);
@@ -121,7 +121,7 @@ static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWor
     B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_min, 0xFF, (size_t)rows * 4, st));
     B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_max, 0x00, (size_t)rows * 4, st));
     dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)ceil_div(m.K, kStatRowsPerCta));
-    rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, ws.enc_min, ws.enc_max, nullptr);
+    rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, ws.enc_min, ws.enc_max);
   }
   B200Q_LAUNCH_OK();
   return B200Q_OK;
@@ -195,60 +195,59 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
   const float clip = (float)clip_ratio;
   unsigned char* zp_rows = layout == B200Q_MATMUL_NBITS ? ws.zp_rows : (unsigned char*)out_zp;
   unsigned char* kn_dst = layout == B200Q_KN_BYTES ? (unsigned char*)out_codes : ws.codes_tmp;
-  const unsigned int* skip = nullptr;   // set on the fused-MSE route: skip fix-up when no early stop
+  const MseControl* fixup_ctl = nullptr;   // set on the fused-MSE route: fix-ups run only if needed
 
   const bool fused = strategy == B200Q_GROUP &&
                      (m.gs == 16 || m.gs == 32 || m.gs == 64 || m.gs == 128) && N % 16 == 0 &&
                      ((uintptr_t)W % 16 == 0) && ((uintptr_t)out_codes % 16 == 0);
-  if (mse) B200Q_CUDA_OK(cudaMemsetAsync(ws.or_mask, 0, 8, st));   // or_mask and proven-mask
+  if (mse) B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
+  const int blocks = (int)ceil_div(s.rows, 256);
 
   if (fused) {
     FusedArgs a;
     a.W = W; a.K = K; a.N = N; a.G = m.G; a.qs = qs; a.clip = clip; a.layout = layout;
     a.out_codes = (unsigned char*)out_codes; a.out_scale = out_scale; a.zp_rows = zp_rows;
-    a.masks = ws.masks; a.or_mask = ws.or_mask;
-    a.enc_min = ws.enc_min; a.enc_max = ws.enc_max;
-    a.run_unless_full = nullptr; a.set_full_when_skipped = nullptr;
+    a.masks = ws.masks; a.enc_min = ws.enc_min; a.enc_max = ws.enc_max;
+    a.ctl = ws.ctl; a.run_if_state = 0;
     if (!mse) {
       launch_fused_gs(a, m.gs, kPlain, st);
       B200Q_LAUNCH_OK();
     } else {
       if (mse != B200Q_MSE_EXACT) {
-        // tier 1+2 in one kernel; its OR of *proven* improvements goes to ws.or_mask[1]
-        FusedArgs t = a;
-        t.or_mask = ws.or_mask + 1;
-        launch_fused_gs(t, m.gs, kTwoTier, st);
+        // optimistic run over all 20 candidates; publishes proven / possible improvement masks
+        launch_fused_gs(a, m.gs, kTwoTier, st);
         B200Q_LAUNCH_OK();
-        a.run_unless_full = ws.or_mask + 1;       // exact kernel only if "no early stop" is unproven
-        a.set_full_when_skipped = ws.or_mask;
+        mse_decide_kernel<<<1, 32, 0, st>>>(ws.ctl);
+        B200Q_LAUNCH_OK();
+        a.run_if_state = kMseRerun;       // the reference stopped early at a known step: redo prefix
+        launch_fused_gs(a, m.gs, kTwoTier, st);
+        B200Q_LAUNCH_OK();
+        a.run_if_state = kMseNeedExact;   // evidence inconclusive: evaluate everything exactly
       }
       launch_fused_gs(a, m.gs, kExact, st);
       B200Q_LAUNCH_OK();
-    }
-    if (mse) {
-      // The fused kernel assumed "no global early stop" (every step improved some row).  If the
-      // OR-mask says otherwise, redo the row decisions for the stop index and requantize; all of
-      // the fix-up kernels return immediately when the mask is full.
-      int blocks = (int)ceil_div(s.rows, 256);
-      mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.or_mask, ws.enc_min, ws.enc_max,
-                                                  s.rows, qs, out_scale, zp_rows, out_mse_info, 1);
+      // If the exact kernel ran and the early stop cut the search short, redo the row decisions
+      // for the stop index and requantize; otherwise these kernels return immediately.
+      mse_finalize_kernel<<<blocks, 256, 0, st>>>(
+          ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows, qs, out_scale, zp_rows, out_mse_info,
+          mse == B200Q_MSE_EXACT ? kFinalizeFusedForcedExact : kFinalizeFused);
       B200Q_LAUNCH_OK();
-      skip = ws.or_mask;
+      fixup_ctl = ws.ctl;
     }
   } else {
     rc = launch_rowstats(W, m, s.rows, ws, st);
     if (rc != B200Q_OK) return rc;
-    int blocks = (int)ceil_div(s.rows, 256);
     if (mse) {
       const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
       dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)m.G);
       dim3 block(32, kMseCandidates);
-      mse_error_table_kernel<<<grid, block, 0, st>>>(W, m, qs, ws.enc_min, ws.enc_max, ws.err, nullptr);
+      mse_error_table_kernel<<<grid, block, 0, st>>>(W, m, qs, ws.enc_min, ws.enc_max, ws.err);
       B200Q_LAUNCH_OK();
-      mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.or_mask, nullptr);
+      mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
       B200Q_LAUNCH_OK();
-      mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.or_mask, ws.enc_min, ws.enc_max,
-                                                  s.rows, qs, out_scale, zp_rows, out_mse_info, 0);
+      mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows,
+                                                  qs, out_scale, zp_rows, out_mse_info,
+                                                  kFinalizeGeneric);
     } else {
       qparams_from_stats_kernel<<<blocks, 256, 0, st>>>(ws.enc_min, ws.enc_max, s.rows, clip, qs,
                                                         out_scale, zp_rows);
@@ -259,16 +258,16 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
   if (!fused || mse) {
     // generic quantize (+ pack): the only route when !fused, the conditional fix-up when fused
     quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, st>>>(W, m, qs, out_scale, zp_rows,
-                                                                  kn_dst, skip);
+                                                                  kn_dst, fixup_ctl);
     B200Q_LAUNCH_OK();
     if (layout == B200Q_PACKED_FLAT) {
       pack4_flat_kernel<<<elementwise_grid((K * N + 1) / 2), 256, 0, st>>>(
-          kn_dst, K * N, (unsigned char*)out_codes, skip);
+          kn_dst, K * N, (unsigned char*)out_codes, fixup_ctl);
       B200Q_LAUNCH_OK();
     } else if (layout == B200Q_MATMUL_NBITS) {
       dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 128));
       pack_matmul_nbits_kernel<<<grid, 256, 0, st>>>(kn_dst, K, N, qs.bits,
-                                                     (unsigned char*)out_codes, skip);
+                                                     (unsigned char*)out_codes, fixup_ctl);
       B200Q_LAUNCH_OK();
     }
   }
@@ -276,6 +275,32 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     pack_zp_matmul_nbits_kernel<<<elementwise_grid(s.rows), 256, 0, st>>>(
         zp_rows, N, m.G, qs.bits, (unsigned char*)out_zp, nullptr);
     B200Q_LAUNCH_OK();
+  }
+  return B200Q_OK;
+}
+
+size_t b200q_rtn_batch_workspace_bytes(const b200q_rtn_job* jobs, int64_t n_jobs, int strategy,
+                                       int64_t group_size, int mse) {
+  size_t need = 0;
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    size_t b = b200q_rtn_workspace_bytes(jobs[i].K, jobs[i].N, strategy, group_size, mse);
+    if (b == 0) return 0;
+    if (b > need) need = b;
+  }
+  return need;
+}
+
+int b200q_rtn_quantize_batch(const b200q_rtn_job* jobs, int64_t n_jobs, int qtype, int strategy,
+                             int64_t group_size, int symmetric, int reduce_range,
+                             double clip_ratio, int mse, int layout, void* workspace,
+                             size_t workspace_bytes, b200q_stream_t stream) {
+  B200Q_REQUIRE(jobs && n_jobs >= 0, B200Q_ERR_INVALID_ARG, "bad job list");
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const b200q_rtn_job& j = jobs[i];
+    int rc = b200q_rtn_quantize(j.W, j.K, j.N, qtype, strategy, group_size, symmetric, reduce_range,
+                                clip_ratio, mse, layout, j.out_codes, j.out_scale, j.out_zp,
+                                j.out_mse_info, workspace, workspace_bytes, stream);
+    if (rc != B200Q_OK) return rc;
   }
   return B200Q_OK;
 }
@@ -299,7 +324,7 @@ int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int s
   const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
   dim3 block(32, kMseCandidates);
-  mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, out_err, nullptr);
+  mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, out_err);
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }
@@ -323,17 +348,17 @@ int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strate
   if (rc != B200Q_OK) return rc;
   int blocks = (int)ceil_div(s.rows, 256);
   if (mse) {
-    B200Q_CUDA_OK(cudaMemsetAsync(ws.or_mask, 0, 4, st));
+    B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
     const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
     dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
     dim3 block(32, kMseCandidates);
-    mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, ws.err, nullptr);
+    mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, ws.err);
     B200Q_LAUNCH_OK();
-    mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.or_mask, nullptr);
+    mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
     B200Q_LAUNCH_OK();
   }
   row_ranges_kernel<<<blocks, 256, 0, st>>>(ws.enc_min, ws.enc_max, mse ? ws.masks : nullptr,
-                                            ws.or_mask, s.rows, (float)clip_ratio, out_min, out_max);
+                                            ws.ctl, s.rows, (float)clip_ratio, out_min, out_max);
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }

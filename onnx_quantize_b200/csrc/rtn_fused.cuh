@@ -42,6 +42,29 @@ __device__ __constant__ float kShrink[kMseCandidates] = {
 
 constexpr unsigned int kAllCandidates = (1u << kMseCandidates) - 1u;   // 0xFFFFF
 
+// Global early stop (utils.py:232-237): the counter is incremented at every step at which NO row
+// improved and is never reset; the loop ends after the step at which it reaches `patience`.
+// Returns the last evaluated step for a given OR of the rows' "improved at step i" masks.
+__host__ __device__ __forceinline__ int mse_stop_index(unsigned int or_mask) {
+  int stalls = 0;
+  for (int i = 0; i < kMseCandidates; ++i) {
+    if (!((or_mask >> i) & 1u)) ++stalls;
+    if (stalls >= kMsePatience) return i;
+  }
+  return kMseCandidates - 1;
+}
+
+// Control block of one MSE quantization (device memory, zeroed before the launch chain).
+struct MseControl {
+  unsigned int or_mask;       // exact kernel: OR of the rows' improvement masks
+  unsigned int proven_or;     // two-tier kernel: improvements that are certain
+  unsigned int possible_or;   // two-tier kernel: improvements that cannot be ruled out
+  int n_cand;                 // candidates the (re-)run of the two-tier kernel evaluates
+  int state;                  // kMseDone / kMseRerun / kMseNeedExact, set by mse_decide_kernel
+  int stop;                   // early-stop index i* reported to the caller
+};
+enum MseState { kMseUndecided = 0, kMseDone = 1, kMseRerun = 2, kMseNeedExact = 3 };
+
 enum FusedMode { kPlain = 0, kExact = 1, kTwoTier = 2 };
 
 // tau of the two-tier search.  Error budget `delta` of an approximate sum relative to the
@@ -62,11 +85,10 @@ struct FusedArgs {
   float* out_scale;
   unsigned char* zp_rows;   // one byte per parameter row
   unsigned int* masks;      // kExact: per-row "improved at step i" bit mask
-  unsigned int* or_mask;    // kExact: OR of all masks;  kTwoTier: OR of the proven-improvement masks
   unsigned int* enc_min;    // kExact: per-row raw min / max (order-preserving encoding), consumed by
   unsigned int* enc_max;    //         the early-stop fix-up (mse_finalize_kernel)
-  const unsigned int* run_unless_full;   // kExact as fallback: return at once if *ptr == 0xFFFFF
-  unsigned int* set_full_when_skipped;   // ... and publish "no early stop" for the fix-up kernels
+  MseControl* ctl;          // MSE modes
+  int run_if_state;         // launch is a no-op unless ctl->state == run_if_state (0: always run)
 };
 
 constexpr int kFusedCols = 64;
@@ -106,13 +128,10 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
   constexpr int M = GS / 8;
   __shared__ __align__(16) unsigned char stage[fused_stage_bytes<GS>()];
 
-  if (MODE == kExact && a.run_unless_full) {
-    if (*a.run_unless_full == kAllCandidates) {
-      if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-        *a.set_full_when_skipped = kAllCandidates;
-      return;
-    }
+  if (MODE != kPlain && a.run_if_state != 0) {
+    if (a.ctl->state != a.run_if_state) return;
   }
+  const int n_cand = (MODE == kTwoTier && a.run_if_state == kMseRerun) ? a.ctl->n_cand : kMseCandidates;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rl = lane & 7, cq = lane >> 3;
@@ -199,12 +218,12 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
     unsigned int any = col_ok ? (improved[0] | improved[1] | improved[2] | improved[3]) : 0u;
     any = __reduce_or_sync(0xffffffffu, any);
     if (lane == 0) {
-      unsigned int cur = *((volatile unsigned int*)a.or_mask);
-      if (any & ~cur) atomicOr(a.or_mask, any);
+      unsigned int cur = *((volatile unsigned int*)&a.ctl->or_mask);
+      if (any & ~cur) atomicOr(&a.ctl->or_mask, any);
     }
   } else {
     // ---- A6, two-tier ----
-    unsigned int proven_any = 0;
+    unsigned int proven_any = 0, possible_any = 0;
     const bool recip = qs.bits == 4;   // 8-bit types keep the IEEE division (see kTierTau)
     int pick[4];                        // best candidate per column
     unsigned int redo[4];               // candidates that need the exact sequence (0 = proven)
@@ -214,9 +233,9 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
       float s1 = INFINITY, s2 = INFINITY, s3 = INFINITY;   // three smallest approximate scores
       int i1 = 0, i2 = 0;
       float runmin = INFINITY;
-      unsigned int proven = 0;
+      unsigned int proven = 0, possible = 0;
 #pragma unroll 1
-      for (int i = 0; i < kMseCandidates; ++i) {
+      for (int i = 0; i < n_cand; ++i) {
         const float p = kShrink[i];
         const QParam cand = qparam_from_range(__fmul_rn(p, lo0), __fmul_rn(p, hi0), qs);
         const float s = cand.scale, inv_s = __frcp_rn(s);
@@ -234,7 +253,8 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-        if (r * (1.0f + kTierTau) < runmin) proven |= 1u << i;   // certainly a new strict minimum
+        if (r * (1.0f + kTierTau) < runmin) proven |= 1u << i;     // certainly a new strict minimum
+        if (r < runmin * (1.0f + kTierTau)) possible |= 1u << i;   // cannot be ruled out
         runmin = fminf(runmin, r);
         if (r < s1) { s3 = s2; s2 = s1; i2 = i1; s1 = r; i1 = i; }
         else if (r < s2) { s3 = s2; s2 = r; i2 = i; }
@@ -243,8 +263,9 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
       const float limit = s1 * (1.0f + kTierTau);
       pick[c] = i1;
       // ambiguous (or non-finite scores): the two best if the third is out of reach, else all
-      redo[c] = (s2 > limit) ? 0u : ((s3 > limit) ? ((1u << i1) | (1u << i2)) : kAllCandidates);
+      redo[c] = (s2 > limit) ? 0u : ((s3 > limit) ? ((1u << i1) | (1u << i2)) : ((1u << n_cand) - 1u));
       proven_any |= proven;
+      possible_any |= possible;
     }
     // exact re-evaluation of the survivors, in candidate order with strict <  (one copy of the
     // exact code for all four columns: the column is selected with compile-time indices)
@@ -287,10 +308,15 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
       const float p = kShrink[pick[c]];
       qp[c] = qparam_from_range(__fmul_rn(p, fminf(mn[c], 0.0f)), __fmul_rn(p, fmaxf(mx[c], 0.0f)), qs);
     }
-    unsigned int any = __reduce_or_sync(0xffffffffu, col_ok ? proven_any : 0u);
-    if (lane == 0) {
-      unsigned int cur = *((volatile unsigned int*)a.or_mask);
-      if (any & ~cur) atomicOr(a.or_mask, any);
+    if (a.run_if_state == 0) {   // the optimistic first run publishes its evidence
+      unsigned int pr = __reduce_or_sync(0xffffffffu, col_ok ? proven_any : 0u);
+      unsigned int po = __reduce_or_sync(0xffffffffu, col_ok ? possible_any : 0u);
+      if (lane == 0) {
+        unsigned int cur = *((volatile unsigned int*)&a.ctl->proven_or);
+        if (pr & ~cur) atomicOr(&a.ctl->proven_or, pr);
+        cur = *((volatile unsigned int*)&a.ctl->possible_or);
+        if (po & ~cur) atomicOr(&a.ctl->possible_or, po);
+      }
     }
   }
 

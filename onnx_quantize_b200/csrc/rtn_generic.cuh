@@ -8,8 +8,15 @@
 #pragma once
 
 #include "common.cuh"
+#include "rtn_fused.cuh"
 
 namespace b200q {
+
+// Fix-up kernels of the exact MSE route carry a control block: they only do work when the early
+// stop actually cut the search short (state kMseNeedExact and stop index < 19).
+__device__ __forceinline__ bool skip_unless(const MseControl* ctl) {
+  return ctl != nullptr && !(ctl->state == kMseNeedExact && ctl->stop < kMseCandidates - 1);
+}
 
 struct RowMap {
   int64_t K, N;
@@ -29,9 +36,7 @@ constexpr int kStatRowsPerCta = 256;
 
 static __global__ void __launch_bounds__(128) rowstats_cols_kernel(const float* __restrict__ W, RowMap m,
                                                             unsigned int* __restrict__ enc_min,
-                                                            unsigned int* __restrict__ enc_max,
-                                                            const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+                                                            unsigned int* __restrict__ enc_max) {
   int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (n >= m.N) return;
   int64_t k0 = (int64_t)blockIdx.y * kStatRowsPerCta;
@@ -72,8 +77,8 @@ static __global__ void qparams_from_stats_kernel(const unsigned int* __restrict_
 static __global__ void __launch_bounds__(256) quantize_rows_kernel(
     const float* __restrict__ W, RowMap m, QSpec qs, const float* __restrict__ scale,
     const unsigned char* __restrict__ zp, unsigned char* __restrict__ out,
-    const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+    const MseControl* ctl) {
+  if (skip_unless(ctl)) return;
   int64_t total = m.K * m.N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -87,8 +92,8 @@ static __global__ void __launch_bounds__(256) quantize_rows_kernel(
 
 // ---- P1: flat nibble packing (core/_pack.py:8-22) -------------------------------------------------
 static __global__ void pack4_flat_kernel(const unsigned char* __restrict__ codes, int64_t n_elements,
-                                  unsigned char* __restrict__ out, const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+                                  unsigned char* __restrict__ out, const MseControl* ctl) {
+  if (skip_unless(ctl)) return;
   int64_t nbytes = (n_elements + 1) / 2;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nbytes;
        j += (int64_t)gridDim.x * blockDim.x) {
@@ -112,8 +117,8 @@ static __global__ void unpack4_flat_kernel(const unsigned char* __restrict__ pac
 // shared memory so that both the read (along N) and the write (along K) are contiguous runs.
 static __global__ void __launch_bounds__(256) pack_matmul_nbits_kernel(
     const unsigned char* __restrict__ codes, int64_t K, int64_t N, int bits,
-    unsigned char* __restrict__ out, const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+    unsigned char* __restrict__ out, const MseControl* ctl) {
+  if (skip_unless(ctl)) return;
   __shared__ unsigned char tile[32][132];
   int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 128;
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -146,8 +151,8 @@ static __global__ void __launch_bounds__(256) pack_matmul_nbits_kernel(
 // low nibble = even g, odd count padded with 0x8.  G == 1 or 8-bit: plain copy.
 static __global__ void pack_zp_matmul_nbits_kernel(const unsigned char* __restrict__ zp_rows, int64_t N,
                                             int64_t G, int bits, unsigned char* __restrict__ out,
-                                            const unsigned int* skip_if_full) {
-  if (skip_if_full && *skip_if_full == 0xFFFFFu) return;
+                                            const MseControl* ctl) {
+  if (skip_unless(ctl)) return;
   bool packed = bits == 4 && G > 1;
   int64_t per_row = packed ? (G + 1) / 2 : G;
   int64_t total = N * per_row;

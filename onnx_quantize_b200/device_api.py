@@ -109,6 +109,65 @@ def rtn_quantize(w: torch.Tensor, quant_type, strategy, group_size=-1, is_symmet
     return (codes, scale, zp, info) if return_info else (codes, scale, zp)
 
 
+def _alloc_outputs(k, n, qt, st, group_size, layout, device):
+    gs, g = resolve_group(k, st, group_size)
+    rows = num_rows(k, n, st, group_size)
+    bits = 4 if qt in (0, 1) else 8
+    if layout == "kn":
+        codes = torch.empty((k, n), dtype=torch.uint8, device=device)
+    elif layout == "packed_flat":
+        codes = torch.empty(((k * n + 1) // 2,), dtype=torch.uint8, device=device)
+    else:
+        codes = torch.empty((n, g, gs * bits // 8), dtype=torch.uint8, device=device)
+    if layout == "matmul_nbits":
+        zp_cols = (g + 1) // 2 if (bits == 4 and g > 1) else g
+        return codes, torch.empty((n, g), dtype=torch.float32, device=device), \
+            torch.empty((n, zp_cols), dtype=torch.uint8, device=device)
+    return codes, torch.empty((rows,), dtype=torch.float32, device=device), \
+        torch.empty((rows,), dtype=torch.uint8, device=device)
+
+
+class RtnBatchPlan:
+    """Pre-built job list for ``rtn_quantize_batch``: output tensors allocated once, reusable."""
+
+    def __init__(self, weights, quant_type, strategy, group_size=-1, is_symmetric=False,
+                 reduce_range=False, clip_ratio=1.0, mse=False, layout="kn"):
+        lib = _lib.load()
+        self.args = (_qt(quant_type), _strategy(strategy), int(group_size or -1),
+                     int(bool(is_symmetric)), int(bool(reduce_range)), float(clip_ratio),
+                     _mse_mode(mse), _lib.LAYOUT[layout])
+        qt, st = self.args[0], self.args[1]
+        self.weights = list(weights)
+        self.outputs = []
+        self.jobs = (_lib.RtnJob * len(self.weights))()
+        for i, w in enumerate(self.weights):
+            k, n = _check_weight(w)
+            out = _alloc_outputs(k, n, qt, st, group_size, layout, w.device)
+            self.outputs.append(out)
+            self.jobs[i] = _lib.RtnJob(w.data_ptr(), k, n, out[0].data_ptr(), out[1].data_ptr(),
+                                       out[2].data_ptr(), None)
+        self.ws_bytes = lib.b200q_rtn_batch_workspace_bytes(self.jobs, len(self.weights), st,
+                                                            self.args[2], self.args[6])
+        if len(self.weights) and self.ws_bytes == 0:
+            raise ValueError("invalid shape / group size in the job list")
+
+    def run(self):
+        lib = _lib.load()
+        ws = dev.workspace(self.ws_bytes)
+        qt, st, gs, sym, rr, clip, mse, lay = self.args
+        rc = lib.b200q_rtn_quantize_batch(self.jobs, len(self.weights), qt, st, gs, sym, rr, clip,
+                                          mse, lay, ws.data_ptr(), ws.numel(), dev.stream_ptr())
+        _lib.check(rc, "b200q_rtn_quantize_batch")
+        return self.outputs
+
+
+def rtn_quantize_batch(weights, quant_type, strategy, group_size=-1, is_symmetric=False,
+                       reduce_range=False, clip_ratio=1.0, mse=False, layout="kn"):
+    """``rtn_quantize`` for a list of weights with one configuration, issued from one C call."""
+    return RtnBatchPlan(weights, quant_type, strategy, group_size, is_symmetric, reduce_range,
+                        clip_ratio, mse, layout).run()
+
+
 def mse_error_table(w: torch.Tensor, quant_type, strategy, group_size=-1, is_symmetric=False,
                     reduce_range=False) -> torch.Tensor:
     """f32 (20, rows): the error sum of every shrink candidate for every parameter row."""

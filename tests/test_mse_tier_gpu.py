@@ -45,7 +45,8 @@ def test_two_tier_equals_exact(cuda, qt, sym, gs, shape):
     b = D.rtn_quantize(w, qt, "group", gs, sym, False, 1.0, "exact", layout=layout, return_info=True)
     for ta, tb in zip(a[:3], b[:3]):
         assert torch.equal(ta, tb)
-    assert a[3].tolist() == [19, 0xFFFFF] and b[3].tolist() == [19, 0xFFFFF]
+    ia, ib = a[3].tolist(), b[3].tolist()
+    assert ia[0] == ib[0] == 19 and (ia[1] & ~ib[1]) == 0   # proven improvements are real ones
 
 
 def test_two_tier_tiny_inputs_take_the_exact_route(cuda):
