@@ -58,14 +58,17 @@ enum b200q_strategy { B200Q_TENSOR = 0, B200Q_CHANNEL = 1, B200Q_GROUP = 2 };
  */
 enum b200q_layout { B200Q_KN_BYTES = 0, B200Q_PACKED_FLAT = 1, B200Q_MATMUL_NBITS = 2 };
 
-/* Hessian contraction precision on the tcgen05 tensor cores. */
+/* Hessian contraction precision: TF32 = one tcgen05 kind::tf32 product (inputs truncated to
+ * tf32), TF32X3 = three products on a hi/lo split of every input (fp32-like accuracy, default),
+ * FP32_SIMT = plain fp32 FMAs on the CUDA cores (any shape; the tensor-core routes need K % 32 == 0
+ * and fall back to it otherwise). */
 /* `mse` argument of the RTN entry points.  ON evaluates the shrink-grid search with the two-tier
  * scheme (approximate scores prove most decisions, the exact float32 sequence settles the rest);
  * EXACT evaluates every candidate with the exact sequence (verification / fallback).  Both give
  * the reference's result. */
 enum b200q_mse_mode { B200Q_MSE_OFF = 0, B200Q_MSE_ON = 1, B200Q_MSE_EXACT = 2 };
 
-enum b200q_precision { B200Q_TF32 = 0, B200Q_TF32X3 = 1 };
+enum b200q_precision { B200Q_TF32 = 0, B200Q_TF32X3 = 1, B200Q_FP32_SIMT = 2 };
 
 /* GPTQ update rule: REFERENCE reproduces gptq.py:198-208 as written (reads the zero triangle of
  * the upper factor: no error propagation); PROPAGATE is GPTQ as published. */

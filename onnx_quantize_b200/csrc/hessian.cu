@@ -1,0 +1,467 @@
+// hessian.cu — H <- beta*H + alpha * X^T X on the tcgen05 tensor cores (kind::tf32, fp32 accumulate in
+// TMEM), replacing `_accumulate_hessian` (core/_algorithms/gptq.py:246-260).
+//
+// X is (T tokens, K channels) row-major fp32, so for an output tile H[i-block, j-block] both MMA
+// operands are slices of the SAME rows of X with the contraction dimension (tokens) as the slow
+// memory dimension: A = X[t, i-block]^T and B = X[t, j-block] are both "MN-major".  TMA loads
+// boxes of 32 channels x TT tokens (128-byte inner extent, SWIZZLE_128B) straight into the
+// canonical MN-major/SW128 UMMA layout — ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units — so no
+// transpose ever happens: LBO = TT*128 B steps to the next 32 channels, SBO = 1024 B to the next 8
+// tokens, one tcgen05.mma consumes 8 tokens (tf32 K = 8) of a 128 x 256 tile.
+//
+// Work decomposition: only tiles that touch the upper triangle are computed; each tile's token
+// range may be split so that every SM has work (units = tiles x splits); the epilogue scales by
+// alpha and adds into H and into the mirrored position with float atomics (H was pre-scaled by
+// beta).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// epilogue (TMEM lanes 32*(warp%4)), and for TF32x3 warps 8-11 split every landed fp32 value
+// into hi = tf32(x) and lo = x - hi so that D += Ah*Bh + Ah*Bl + Al*Bh recovers fp32 accuracy.
+// Two 256-column accumulators (all 512 TMEM columns) double-buffer MMA against the epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200q {
+
+namespace {
+
+constexpr int kTileM = 128;          // output rows per tile (TMEM lanes)
+constexpr int kTileN = 256;          // output columns per tile (TMEM columns)
+constexpr int kTT = 32;              // tokens per pipeline stage
+constexpr int kBoxCols = 32;         // channels per TMA box row (128 B)
+constexpr int kABytes = kTileM * kTT * 4;    // 16 KB
+constexpr int kBBytes = kTileN * kTT * 4;    // 32 KB
+constexpr int kStageBytes1 = kABytes + kBBytes;          // tf32: 48 KB
+constexpr int kStageBytes3 = 2 * (kABytes + kBBytes);    // tf32x3: hi + lo, 96 KB
+constexpr int kStages1 = 4;
+constexpr int kStages3 = 2;
+constexpr int kThreads1 = 256;       // warps 0..7
+constexpr int kThreads3 = 384;       // + converter warps 8..11
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+      "%3, %4}], [%5];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// SM100 shared-memory matrix descriptor, MN-major operand, SWIZZLE_128B:
+// bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout = 2
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes,
+                                                       uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::tf32 instruction descriptor: fp32 accumulate, A and B tf32, both MN-major, M x N
+constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct HessianParams {
+  int64_t T, K;
+  float alpha;
+  float* H;
+  int n_ib;            // 128-row blocks
+  int n_jb;            // 256-column blocks
+  int n_tiles;         // tiles touching the upper triangle
+  int splits;          // token-range splits per tile
+  int64_t t_per_split; // multiple of kTT
+  int precision;
+};
+
+// unit -> (ib, jb, split).  Tiles are enumerated row-block by row-block; a tile is kept when its
+// last column 256*jb+255 reaches the first row 128*ib of the block (it touches j >= i).
+__device__ __forceinline__ void decode_unit(const HessianParams& p, int unit, int& ib, int& jb, int& sp) {
+  int tile = unit / p.splits;
+  sp = unit - tile * p.splits;
+  int acc = 0;
+  for (ib = 0; ib < p.n_ib; ++ib) {
+    int first_jb = (ib * kTileM) / kTileN;
+    int cnt = p.n_jb - first_jb;
+    if (tile < acc + cnt) { jb = first_jb + (tile - acc); return; }
+    acc += cnt;
+  }
+  ib = 0; jb = 0;
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? kThreads3 : kThreads1, 1)
+hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) {
+  constexpr int kStages = X3 ? kStages3 : kStages1;
+  constexpr int kStageBytes = X3 ? kStageBytes3 : kStageBytes1;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: stage buffers (1024-aligned), then barriers
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);   // TMA landed
+  uint64_t* conv_bar = full_bar + kStages;                          // X3: hi/lo written
+  uint64_t* empty_bar = conv_bar + kStages;                         // MMAs of the stage retired
+  uint64_t* tmem_full = empty_bar + kStages;                        // [2] accumulator complete
+  uint64_t* tmem_empty = tmem_full + 2;                             // [2] accumulator drained
+  uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = p.n_tiles * p.splits;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&conv_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int ib, jb, sp;
+        decode_unit(p, unit, ib, jb, sp);
+        const int64_t t0 = (int64_t)sp * p.t_per_split;
+        const int64_t t1 = min(t0 + p.t_per_split, p.T);
+        for (int64_t t = t0; t < t1; t += kTT) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sb = smem + stage * kStageBytes;
+          mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          // A: 128 channels = 4 column blocks; B: 256 channels = two boxes of 4 column blocks
+          tma_load_3d(sb, &tmap, &full_bar[stage], 0, (int)t, ib * (kTileM / kBoxCols));
+          tma_load_3d(sb + kABytes, &tmap, &full_bar[stage], 0, (int)t, jb * (kTileN / kBoxCols));
+          tma_load_3d(sb + kABytes + kABytes, &tmap, &full_bar[stage], 0, (int)t,
+                      jb * (kTileN / kBoxCols) + 4);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTileM, kTileN);
+      constexpr uint32_t lbo = kTT * 128, sbo = 1024;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int ib, jb, sp;
+        decode_unit(p, unit, ib, jb, sp);
+        const int64_t t0 = (int64_t)sp * p.t_per_split;
+        const int64_t t1 = min(t0 + p.t_per_split, p.T);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + (uint32_t)acc * kTileN;
+        uint32_t accumulate = 0;
+        for (int64_t t = t0; t < t1; t += kTT) {
+          mbar_wait(X3 ? &conv_bar[stage] : &full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sbb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kTT / 8; ++k) {
+            const uint64_t ah = umma_desc_mn_sw128(sa + k * 1024, lbo, sbo);
+            const uint64_t bh = umma_desc_mn_sw128(sbb + k * 1024, lbo, sbo);
+            umma_tf32(d, ah, bh, idesc, accumulate);
+            accumulate = 1;
+            if (X3) {
+              const uint64_t al = umma_desc_mn_sw128(sa + (kABytes + kBBytes) + k * 1024, lbo, sbo);
+              const uint64_t bl = umma_desc_mn_sw128(sbb + (kABytes + kBBytes) + k * 1024, lbo, sbo);
+              umma_tf32(d, ah, bl, idesc, 1);
+              umma_tf32(d, al, bh, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue: TMEM -> registers -> alpha * acc added into H and its mirror =====
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      int ib, jb, sp;
+      decode_unit(p, unit, ib, jb, sp);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t i = (int64_t)ib * kTileM + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTileN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + c0), r);
+        const int64_t j0 = (int64_t)jb * kTileN + c0;
+        if (i < p.K) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int64_t j = j0 + c;
+            if (j < p.K && j >= i) {
+              const float v = p.alpha * __uint_as_float(r[c]);
+              atomicAdd(&p.H[i * p.K + j], v);
+              if (j > i) atomicAdd(&p.H[j * p.K + i], v);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (X3 && warp >= 8) {
+    // ===== converter (TF32x3): x -> hi = tf32(x) in place, lo = x - hi in the second buffer =====
+    const int ct = threadIdx.x - 256;   // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      int ib, jb, sp;
+      decode_unit(p, unit, ib, jb, sp);
+      const int64_t t0 = (int64_t)sp * p.t_per_split;
+      const int64_t t1 = min(t0 + p.t_per_split, p.T);
+      for (int64_t t = t0; t < t1; t += kTT) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* hi = (float4*)(smem + stage * kStageBytes);
+        float4* lo = (float4*)(smem + stage * kStageBytes + kABytes + kBBytes);
+#pragma unroll 4
+        for (int v = ct; v < (kABytes + kBBytes) / 16; v += 128) {
+          float4 x = hi[v], h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+          hi[v] = h;
+          lo[v] = l;
+        }
+        // generic-proxy writes must be visible to the tensor core's async proxy reads
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&conv_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
+__global__ void scale_inplace_kernel(float* h, int64_t n, float beta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    h[i] *= beta;
+}
+
+// Shape-agnostic SIMT route (K not a multiple of 32, or unaligned X): one thread per H element of
+// the upper triangle, fp32 FMA over tokens.  Exact fp32 semantics; used for small / odd problems.
+__global__ void hessian_simt_kernel(const float* __restrict__ X, int64_t T, int64_t K, float alpha,
+                                    float* __restrict__ H) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+  if (j0 + 31 < i0) return;   // strictly lower block
+  float acc = 0.f;
+  for (int64_t t0 = 0; t0 < T; t0 += 32) {
+    int64_t t = t0 + ty;
+    sa[ty][tx] = (t < T && i0 + tx < K) ? X[t * K + i0 + tx] : 0.f;
+    sb[ty][tx] = (t < T && j0 + tx < K) ? X[t * K + j0 + tx] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(sa[k][ty], sb[k][tx], acc);
+    __syncthreads();
+  }
+  const int64_t i = i0 + ty, j = j0 + tx;
+  if (i < K && j < K && j >= i) {
+    const float v = alpha * acc;
+    H[i * K + j] += v;
+    if (j > i) H[j * K + i] += v;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)sym;
+  return fn;
+}
+
+}  // namespace
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+size_t b200q_hessian_workspace_bytes(int64_t T, int64_t K, int precision) {
+  (void)T; (void)K; (void)precision;
+  return 256;   // nothing needed today; kept in the ABI so a split-K reduction buffer can be added
+}
+
+int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, float beta, float* H,
+                             int precision, void* workspace, size_t workspace_bytes,
+                             b200q_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200Q_REQUIRE(X && H && T > 0 && K > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  B200Q_REQUIRE(precision == B200Q_TF32 || precision == B200Q_TF32X3 || precision == B200Q_FP32_SIMT,
+                B200Q_ERR_INVALID_ARG, "unknown precision %d", precision);
+  B200Q_REQUIRE(T < (1ll << 31) && K < (1ll << 31), B200Q_ERR_UNSUPPORTED, "T and K must fit in int32");
+  // H <- beta * H
+  if (beta == 0.0f) {
+    B200Q_CUDA_OK(cudaMemsetAsync(H, 0, (size_t)K * K * sizeof(float), st));
+  } else if (beta != 1.0f) {
+    scale_inplace_kernel<<<kNumSMs * 8, 256, 0, st>>>(H, K * K, beta);
+    B200Q_LAUNCH_OK();
+  }
+  const bool tensor_ok = precision != B200Q_FP32_SIMT && K % kBoxCols == 0 && ((uintptr_t)X % 16 == 0);
+  if (!tensor_ok) {
+    dim3 grid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(K, 32)), block(32, 32);
+    hessian_simt_kernel<<<grid, block, 0, st>>>(X, T, K, alpha, H);
+    B200Q_LAUNCH_OK();
+    return B200Q_OK;
+  }
+
+  EncodeTiledFn encode = get_encode_fn();
+  B200Q_REQUIRE(encode != nullptr, B200Q_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  // X viewed as 3-D: (32 channels, T tokens, K/32 channel blocks) so that one box lands as
+  // [channel block][token][32 channels] = the MN-major canonical layout
+  CUtensorMap tmap;
+  cuuint64_t dims[3] = {(cuuint64_t)kBoxCols, (cuuint64_t)T, (cuuint64_t)(K / kBoxCols)};
+  cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)kBoxCols * sizeof(float)};
+  cuuint32_t box[3] = {kBoxCols, kTT, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)X, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200Q_REQUIRE(cr == CUDA_SUCCESS, B200Q_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  HessianParams p;
+  p.T = T; p.K = K; p.alpha = alpha; p.H = H; p.precision = precision;
+  p.n_ib = (int)ceil_div(K, kTileM);
+  p.n_jb = (int)ceil_div(K, kTileN);
+  p.n_tiles = 0;
+  for (int ib = 0; ib < p.n_ib; ++ib) p.n_tiles += p.n_jb - (ib * kTileM) / kTileN;
+  // split the token range so that every SM gets work, but keep >= 64 stages per unit
+  const int64_t stages_total = ceil_div(T, kTT);
+  int splits = 1;
+  if (p.n_tiles < 2 * kNumSMs) {
+    splits = (int)ceil_div(2 * kNumSMs, p.n_tiles);
+    int64_t max_splits = stages_total / 64;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = (int)max_splits;
+  }
+  p.splits = splits;
+  p.t_per_split = ceil_div(stages_total, splits) * kTT;
+  p.splits = (int)ceil_div(T, p.t_per_split);
+  const int n_units = p.n_tiles * p.splits;
+  const int grid = n_units < kNumSMs ? n_units : kNumSMs;
+
+  if (precision == B200Q_TF32X3) {
+    const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024 + 256;
+    B200Q_CUDA_OK(cudaFuncSetAttribute(hessian_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    hessian_kernel<true><<<grid, kThreads3, smem, st>>>(tmap, p);
+  } else {
+    const size_t smem = (size_t)kStages1 * kStageBytes1 + 1024 + 256;
+    B200Q_CUDA_OK(cudaFuncSetAttribute(hessian_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    hessian_kernel<false><<<grid, kThreads1, smem, st>>>(tmap, p);
+  }
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+}  // extern "C"
