@@ -76,16 +76,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-// SM100 shared-memory matrix descriptor, MN-major operand, SWIZZLE_128B:
-// bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout = 2
+// SM100 shared-memory matrix descriptor, MN-major tf32 operand.  32-bit MN-major operands have
+// exactly one legal swizzled layout, SWIZZLE_128B_BASE32B (layout type 1): 128-byte rows (32
+// channels of one token) whose 32-byte chunks are XOR-ed with (row & 3) — what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  In 16-byte units the canonical form is
+// ((8,n),(4,k)):((1,LBO),(8,SBO)): LBO = stride between 32-channel blocks, SBO = stride between
+// groups of 4 tokens.  Bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1,
+// [61,64) layout type.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes,
-                                                       uint32_t sbo_bytes) {
+                                                       uint32_t sbo_bytes, uint32_t layout_type = 1) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -134,7 +139,16 @@ struct HessianParams {
   int splits;          // token-range splits per tile
   int64_t t_per_split; // multiple of kTT
   int precision;
+#ifdef B200Q_HESSIAN_PROBE
+  float* dbg_acc;      // [128][256] raw accumulators of unit 0
+  float* dbg_smem;     // first stage as landed (kStageBytes1 bytes)
+  uint32_t dbg_idesc, dbg_lbo, dbg_sbo, dbg_layout;   // 0 = default
+#endif
 };
+#ifdef B200Q_HESSIAN_PROBE
+struct HessianProbe { float* acc; float* smem; uint32_t idesc, lbo, sbo, layout; int tma_swizzle; };
+HessianProbe g_probe = {nullptr, nullptr, 0, 0, 0, 0, 0};
+#endif
 
 // unit -> (ib, jb, split).  Tiles are enumerated row-block by row-block; a tile is kept when its
 // last column 256*jb+255 reaches the first row 128*ib of the block (it touches j >= i).
@@ -216,8 +230,14 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
+#ifdef B200Q_HESSIAN_PROBE
+      const uint32_t idesc = p.dbg_idesc ? p.dbg_idesc : umma_idesc_tf32(kTileM, kTileN);
+      const uint32_t lbo = p.dbg_lbo ? p.dbg_lbo : kTT * 128, sbo = p.dbg_sbo ? p.dbg_sbo : 512;
+      const uint32_t lt = p.dbg_layout ? p.dbg_layout : 1;
+#else
       constexpr uint32_t idesc = umma_idesc_tf32(kTileM, kTileN);
-      constexpr uint32_t lbo = kTT * 128, sbo = 1024;
+      constexpr uint32_t lbo = kTT * 128, sbo = 512, lt = 1;
+#endif
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -234,17 +254,23 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
         for (int64_t t = t0; t < t1; t += kTT) {
           mbar_wait(X3 ? &conv_bar[stage] : &full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef B200Q_HESSIAN_PROBE
+          if (p.dbg_smem && unit == 0 && t == t0) {
+            const float* src = (const float*)(smem + stage * kStageBytes);
+            for (int v = 0; v < kStageBytes1 / 4; ++v) p.dbg_smem[v] = src[v];
+          }
+#endif
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sbb = sa + kABytes;
 #pragma unroll
           for (int k = 0; k < kTT / 8; ++k) {
-            const uint64_t ah = umma_desc_mn_sw128(sa + k * 1024, lbo, sbo);
-            const uint64_t bh = umma_desc_mn_sw128(sbb + k * 1024, lbo, sbo);
+            const uint64_t ah = umma_desc_mn_sw128(sa + k * 1024, lbo, sbo, lt);
+            const uint64_t bh = umma_desc_mn_sw128(sbb + k * 1024, lbo, sbo, lt);
             umma_tf32(d, ah, bh, idesc, accumulate);
             accumulate = 1;
             if (X3) {
-              const uint64_t al = umma_desc_mn_sw128(sa + (kABytes + kBBytes) + k * 1024, lbo, sbo);
-              const uint64_t bl = umma_desc_mn_sw128(sbb + (kABytes + kBBytes) + k * 1024, lbo, sbo);
+              const uint64_t al = umma_desc_mn_sw128(sa + (kABytes + kBBytes) + k * 1024, lbo, sbo, lt);
+              const uint64_t bl = umma_desc_mn_sw128(sbb + (kABytes + kBBytes) + k * 1024, lbo, sbo, lt);
               umma_tf32(d, ah, bl, idesc, 1);
               umma_tf32(d, al, bh, idesc, 1);
             }
@@ -272,6 +298,10 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + c0), r);
         const int64_t j0 = (int64_t)jb * kTileN + c0;
+#ifdef B200Q_HESSIAN_PROBE
+        if (p.dbg_acc && unit == 0)
+          for (int c = 0; c < 32; ++c) p.dbg_acc[(q * 32 + lane) * kTileN + c0 + c] = __uint_as_float(r[c]);
+#endif
         if (i < p.K) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -423,8 +453,12 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
   cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)kBoxCols * sizeof(float)};
   cuuint32_t box[3] = {kBoxCols, kTT, 4};
   cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+#ifdef B200Q_HESSIAN_PROBE
+  if (g_probe.tma_swizzle) swz = (CUtensorMapSwizzle)g_probe.tma_swizzle;
+#endif
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)X, dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200Q_REQUIRE(cr == CUDA_SUCCESS, B200Q_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
@@ -448,6 +482,10 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
   p.splits = (int)ceil_div(T, p.t_per_split);
   const int n_units = p.n_tiles * p.splits;
   const int grid = n_units < kNumSMs ? n_units : kNumSMs;
+#ifdef B200Q_HESSIAN_PROBE
+  p.dbg_acc = g_probe.acc; p.dbg_smem = g_probe.smem;
+  p.dbg_idesc = g_probe.idesc; p.dbg_lbo = g_probe.lbo; p.dbg_sbo = g_probe.sbo; p.dbg_layout = g_probe.layout;
+#endif
 
   if (precision == B200Q_TF32X3) {
     const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024 + 256;
