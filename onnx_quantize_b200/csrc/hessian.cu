@@ -4,15 +4,17 @@
 // X is (T tokens, K channels) row-major fp32, so for an output tile H[i-block, j-block] both MMA
 // operands are slices of the SAME rows of X with the contraction dimension (tokens) as the slow
 // memory dimension: A = X[t, i-block]^T and B = X[t, j-block] are both "MN-major".  TMA loads
-// boxes of 32 channels x TT tokens (128-byte inner extent, SWIZZLE_128B) straight into the
-// canonical MN-major/SW128 UMMA layout — ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units — so no
-// transpose ever happens: LBO = TT*128 B steps to the next 32 channels, SBO = 1024 B to the next 8
-// tokens, one tcgen05.mma consumes 8 tokens (tf32 K = 8) of a 128 x 256 tile.
+// boxes of 32 channels x TT tokens (128-byte inner extent, SWIZZLE_128B_ATOM_32B) straight into the
+// only swizzled layout tcgen05 accepts for 32-bit MN-major operands, SWIZZLE_128B_BASE32B —
+// ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units — so no transpose ever happens: LBO = TT*128 B
+// steps to the next 32 channels, SBO = 512 B to the next 4 tokens, one tcgen05.mma consumes 8 tokens
+// (tf32 K = 8) of a 128 x 256 tile.  (Measured on B200: the plain SWIZZLE_128B layout type with
+// MN-major tf32 silently yields zeros; tools/probe_hessian.cu is the probe that showed it.)
 //
 // Work decomposition: only tiles that touch the upper triangle are computed; each tile's token
 // range may be split so that every SM has work (units = tiles x splits); the epilogue scales by
-// alpha and adds into H and into the mirrored position with float atomics (H was pre-scaled by
-// beta).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// alpha and adds into the upper triangle of H with float atomics (H was pre-scaled by beta); a
+// mirror kernel then copies it below the diagonal, so H is exactly symmetric.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
 // epilogue (TMEM lanes 32*(warp%4)), and for TF32x3 warps 8-11 split every landed fp32 value
 // into hi = tf32(x) and lo = x - hi so that D += Ah*Bh + Ah*Bl + Al*Bh recovers fp32 accuracy.
 // Two 256-column accumulators (all 512 TMEM columns) double-buffer MMA against the epilogue.
@@ -153,8 +155,10 @@ HessianProbe g_probe = {nullptr, nullptr, 0, 0, 0, 0, 0};
 // unit -> (ib, jb, split).  Tiles are enumerated row-block by row-block; a tile is kept when its
 // last column 256*jb+255 reaches the first row 128*ib of the block (it touches j >= i).
 __device__ __forceinline__ void decode_unit(const HessianParams& p, int unit, int& ib, int& jb, int& sp) {
-  int tile = unit / p.splits;
-  sp = unit - tile * p.splits;
+  // split-major: consecutive units are different tiles over the SAME token slab, so the CTAs that
+  // run together stream one slab of X through L2 (read from HBM once)
+  sp = unit / p.n_tiles;
+  int tile = unit - sp * p.n_tiles;
   int acc = 0;
   for (ib = 0; ib < p.n_ib; ++ib) {
     int first_jb = (ib * kTileM) / kTileN;
@@ -302,14 +306,20 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
         if (p.dbg_acc && unit == 0)
           for (int c = 0; c < 32; ++c) p.dbg_acc[(q * 32 + lane) * kTileN + c0 + c] = __uint_as_float(r[c]);
 #endif
-        if (i < p.K) {
+        if (i < p.K && j0 < p.K && j0 + 31 >= i) {   // K % 32 == 0: a 32-column run is all in or all out
+          float* dst = p.H + i * p.K + j0;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int64_t j = j0 + c;
-            if (j < p.K && j >= i) {
-              const float v = p.alpha * __uint_as_float(r[c]);
-              atomicAdd(&p.H[i * p.K + j], v);
-              if (j > i) atomicAdd(&p.H[j * p.K + i], v);
+          for (int c = 0; c < 32; c += 4) {
+            const float v0 = p.alpha * __uint_as_float(r[c]), v1 = p.alpha * __uint_as_float(r[c + 1]);
+            const float v2 = p.alpha * __uint_as_float(r[c + 2]), v3 = p.alpha * __uint_as_float(r[c + 3]);
+            if (j0 + c >= i) {            // whole quad on or above the diagonal: one 16-byte reduction
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v0), "f"(v1),
+                           "f"(v2), "f"(v3)
+                           : "memory");
+            } else if (j0 + c + 3 >= i) { // the quad straddles the diagonal
+              if (j0 + c + 1 >= i) atomicAdd(dst + c + 1, v1);
+              if (j0 + c + 2 >= i) atomicAdd(dst + c + 2, v2);
+              atomicAdd(dst + c + 3, v3);
             }
           }
         }
@@ -358,6 +368,24 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
   }
 }
 
+// H[j][i] <- H[i][j] for j > i: the contraction only accumulates the upper triangle, so the result
+// is exactly symmetric whatever order the split-token partial sums arrived in.
+__global__ void mirror_upper_kernel(float* __restrict__ H, int64_t K) {
+  __shared__ float tile[32][33];
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < K && j < K) ? H[i * K + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t j = bj * 32 + r, i = bi * 32 + tx;   // writes H[j][i] = upper H[i][j] = tile[tx][r]
+    if (i < K && j < K && j > i) H[j * K + i] = tile[tx][r];
+  }
+}
+
 __global__ void scale_inplace_kernel(float* h, int64_t n, float beta) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
@@ -383,11 +411,7 @@ __global__ void hessian_simt_kernel(const float* __restrict__ X, int64_t T, int6
     __syncthreads();
   }
   const int64_t i = i0 + ty, j = j0 + tx;
-  if (i < K && j < K && j >= i) {
-    const float v = alpha * acc;
-    H[i * K + j] += v;
-    if (j > i) H[j * K + i] += v;
-  }
+  if (i < K && j < K && j >= i) H[i * K + j] += alpha * acc;   // upper triangle; mirrored afterwards
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -441,6 +465,8 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
     dim3 grid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(K, 32)), block(32, 32);
     hessian_simt_kernel<<<grid, block, 0, st>>>(X, T, K, alpha, H);
     B200Q_LAUNCH_OK();
+    mirror_upper_kernel<<<grid, dim3(32, 8), 0, st>>>(H, K);
+    B200Q_LAUNCH_OK();
     return B200Q_OK;
   }
 
@@ -468,17 +494,15 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
   p.n_jb = (int)ceil_div(K, kTileN);
   p.n_tiles = 0;
   for (int ib = 0; ib < p.n_ib; ++ib) p.n_tiles += p.n_jb - (ib * kTileM) / kTileN;
-  // split the token range so that every SM gets work, but keep >= 64 stages per unit
+  // Token chunk per unit.  The tensor core adds into the fp32 TMEM accumulator with truncation, so a
+  // chain of n MMAs carries a bias of about n * 2^-25 relative (measured on B200); every unit ends
+  // with a round-to-nearest reduction into H, so the chunk length bounds the bias: 512 tokens
+  // (192 MMAs, ~1e-5 measured) for TF32x3, 4096 tokens for TF32 whose input truncation is 1e-3 anyway.
+  // Short inputs are split further so that every SM has work.
   const int64_t stages_total = ceil_div(T, kTT);
-  int splits = 1;
-  if (p.n_tiles < 2 * kNumSMs) {
-    splits = (int)ceil_div(2 * kNumSMs, p.n_tiles);
-    int64_t max_splits = stages_total / 64;
-    if (max_splits < 1) max_splits = 1;
-    if (splits > max_splits) splits = (int)max_splits;
-  }
-  p.splits = splits;
-  p.t_per_split = ceil_div(stages_total, splits) * kTT;
+  int64_t chunk_stages = precision == B200Q_TF32X3 ? 512 / kTT : 4096 / kTT;
+  while (chunk_stages > 4 && p.n_tiles * ceil_div(stages_total, chunk_stages) < 2 * kNumSMs) chunk_stages /= 2;
+  p.t_per_split = chunk_stages * kTT;
   p.splits = (int)ceil_div(T, p.t_per_split);
   const int n_units = p.n_tiles * p.splits;
   const int grid = n_units < kNumSMs ? n_units : kNumSMs;
@@ -499,6 +523,11 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
     hessian_kernel<false><<<grid, kThreads1, smem, st>>>(tmap, p);
   }
   B200Q_LAUNCH_OK();
+  {
+    dim3 mgrid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(K, 32));
+    mirror_upper_kernel<<<mgrid, dim3(32, 8), 0, st>>>(H, K);
+    B200Q_LAUNCH_OK();
+  }
   return B200Q_OK;
 }
 

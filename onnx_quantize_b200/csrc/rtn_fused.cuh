@@ -68,12 +68,13 @@ enum MseState { kMseUndecided = 0, kMseDone = 1, kMseRerun = 2, kMseNeedExact = 
 enum FusedMode { kPlain = 0, kExact = 1, kTwoTier = 2 };
 
 // tau of the two-tier search.  Error budget `delta` of an approximate sum relative to the
-// reference's float32 sum: |d|^2.4 through lg2.approx/ex2.approx <= 8e-6 (measured on B200 by
+// reference's float32 sum: |d|^2.4 through lg2.approx/ex2.approx <= 1e-5 for |d| in [1e-12, 1e4]
+// (measured on B200: 9.2e-6 worst, at the small end where 2.4*lg2 is largest — asserted by
 // tests/test_mse_tier_gpu.py through b200q_debug_pow_approx), float32 accumulation of <= 128
 // non-negative terms 1.2e-6, rounding-point flips of x*(1/s) for 4-bit types <= 5e-6 (group of
 // 16) — 8-bit types keep the IEEE division so no flip exists —, the reference's own np.power /
-// pairwise-sum rounding 5e-7.  delta <= 1.5e-5, tau = 3.5e-5 > 2 delta / (1 - delta).
-constexpr float kTierTau = 3.5e-5f;
+// pairwise-sum rounding 5e-7.  delta <= 1.7e-5, tau = 4e-5 > 2 delta / (1 - delta) = 3.4e-5.
+constexpr float kTierTau = 4.0e-5f;
 
 struct FusedArgs {
   const float* W;

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_pow_approx_error_bound(cuda):
-    """delta budget of rtn_fused.cuh::kTierTau assumes <= 8e-6 relative error over the range of
+    """delta budget of rtn_fused.cuh::kTierTau assumes <= 1e-5 relative error over the range of
     residuals a quantization error can take (|d| from 1e-12 to 1e4)."""
     g = torch.Generator(device=cuda)
     g.manual_seed(0)
@@ -25,7 +25,7 @@ def test_pow_approx_error_bound(cuda):
         exact = x.to(torch.float64) ** float(np.float32(2.4))
         rel = ((approx - exact).abs() / exact).max().item()
         worst = max(worst, rel)
-    assert worst < 8e-6, worst
+    assert worst < 1e-5, worst
     z = D.debug_pow_approx(torch.zeros(4, device=cuda))
     assert torch.all(z == 0)
 
