@@ -204,6 +204,48 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
                              float* H, int precision, void* workspace, size_t workspace_bytes,
                              b200q_stream_t stream);
 
+/* The inverse-Hessian factor — replaces gptq.py:119-150: dead channels (diag(H) == 0 -> 1),
+ * optional act-order permutation (argsort(diag(H))[::-1]), damping by percdamp * mean(diag(H)),
+ * and `cholesky -> inv -> cholesky(H^-T H^-1).T`.
+ *   H       (K,K) f32, read only
+ *   U       (K,K) f32 out: upper triangular, U^T U = (H[perm][:,perm] + damp*I)^-1
+ *   perm    int32[K] out: row order of the loop (identity unless actorder)
+ *   dead    uint8[K] out: 1 where diag(H) == 0 (the caller zeroes those rows of W, gptq.py:121)
+ *   status  int32[1] out (device): 0, or B200Q_NOT_POSITIVE_DEFINITE — U is then the identity,
+ *           the reference's "fall back to round-to-nearest" (gptq.py:143-150)
+ * One Cholesky and one triangular inverse of the index-reversed matrix give the same U as the
+ * reference's three LAPACK calls; the block products run through the tensor cores
+ * with `precision` (B200Q_TF32X3 recommended; B200Q_FP32_SIMT = CUDA cores). */
+size_t b200q_hinv_workspace_bytes(int64_t K);
+int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int actorder, float* U,
+                              int32_t* perm, unsigned char* dead, int32_t* status, int precision,
+                              void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/* The GPTQ block loop and epilogue — replaces `_gptq` (gptq.py:76-243) given U / perm / dead of
+ * b200q_hinv_cholesky_upper.  Arguments as b200q_rtn_quantize plus
+ *   group_size  > 0: per-output-channel parameters are recomputed every group_size rows inside the
+ *               loop, whatever the strategy (gptq.py:168-184); -1 / 0: the whole-matrix parameters
+ *   block_size  lazy-batch block (gptq.py:153), any positive value
+ *   mode        enum b200q_gptq_mode
+ *   out_codes   (K,N) one byte per element; out_scale / out_zp are the parameters the reference
+ *               returns: recomputed from the dequantized result with `strategy` (gptq.py:219-231)
+ *   out_deq     optional (K,N) f32: the dequantized weights Q of the loop (may be NULL) */
+size_t b200q_gptq_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t group_size, int mse,
+                                  int64_t block_size);
+int b200q_gptq_quantize(const float* W, int64_t K, int64_t N, const float* U, const int32_t* perm,
+                        const unsigned char* dead, int qtype, int strategy, int64_t group_size,
+                        int symmetric, int reduce_range, double clip_ratio, int mse,
+                        int64_t block_size, int mode, int precision, void* out_codes,
+                        float* out_scale, void* out_zp, float* out_deq, void* workspace,
+                        size_t workspace_bytes, b200q_stream_t stream);
+
+/* D (M,N; ldd) <- [D +] alpha * A^T B, A (T,M; lda), B (T,N; ldb) row-major f32: the dense product
+ * of the GPTQ path (Cholesky panels, triangular inverse, block propagation gptq.py:208), exported
+ * for tests.  accumulate: 0 overwrite / 1 add; precision: enum b200q_precision. */
+int b200q_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd,
+                  int64_t T, int64_t M, int64_t N, float alpha, int accumulate, int precision,
+                  b200q_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

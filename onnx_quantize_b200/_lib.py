@@ -72,6 +72,15 @@ _SIGNATURES = {
 _OPTIONAL_SIGNATURES = {
     "b200q_hessian_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "b200q_hessian_accumulate": (_i32, [_ptr, _i64, _i64, _f32, _f32, _ptr, _i32, _ptr, _sz, _ptr]),
+    "b200q_hinv_workspace_bytes": (_sz, [_i64]),
+    "b200q_hinv_cholesky_upper": (_i32, [_ptr, _i64, _f64, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr,
+                                          _sz, _ptr]),
+    "b200q_gptq_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32, _i64]),
+    "b200q_gptq_quantize": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i64, _i32, _i32,
+                                    _f64, _i32, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _sz,
+                                    _ptr]),
+    "b200q_gemm_tn": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _f32, _i32, _i32,
+                              _ptr]),
 }
 
 

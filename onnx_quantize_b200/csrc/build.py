@@ -20,6 +20,8 @@ SOURCES = {
 }
 OPTIONAL = {
     "hessian.cu": [],
+    "gemm_tn.cu": [],
+    "gemm_tn_tc.cu": [],
     "linalg.cu": [],
     "gptq.cu": ["-fmad=false"],
 }

@@ -1,0 +1,279 @@
+// linalg.cu — the Hessian-inverse factor of GPTQ: replaces gptq.py:119-150 (`dead` masking,
+// act-order permutation, damping, cholesky -> inv -> cholesky(H^-T H^-1).T).
+//
+// The reference obtains U (upper, U^T U = H^-1) through three LAPACK calls.  The same U follows
+// from ONE Cholesky and ONE triangular inverse of the index-reversed matrix: with J the reversal
+// permutation, J H J = C^T C (C upper)  =>  H = (J C^T J)(J C J) = R R^T with R = J C^T J upper,
+// hence H^-1 = R^-T R^-1 and U = R^-1 = J C^-T J — the point reflection of the lower-triangular
+// C^-T.  (U is unique: upper triangular with positive diagonal.)  Half the flops of the
+// reference's route and no squaring of the condition number.
+//
+// Blocked, 128 columns at a time; every large product is a gemm_tn (dense.cuh):
+//   potrf : diag block -> C_jj and C_jj^-1 (one CTA, shared memory);  row panel P <- C_jj^-T P;
+//           trailing (upper) <- trailing - P^T P
+//   trtri : V^T = C^-T (lower) row block by row block:
+//           V^T[j, j] = (C_jj^-1)^T;  tmp = C[0:j, j]^T V^T[0:j, 0:j];  V^T[j, 0:j] = -(C_jj^-1)^T tmp
+// A non-positive or NaN pivot raises the status flag; U is then the identity (gptq.py:143-150).
+#include "dense.cuh"
+
+namespace b200q {
+
+namespace {
+
+constexpr int kNB = 128;            // block size of the factorization
+constexpr int kPitch = kNB + 1;     // shared-memory row pitch (conflict-free column access)
+
+// ---- diagonal statistics: dead channels, damping ------------------------------------------------
+// out_diag[i] = diag with dead entries set to 1 (gptq.py:119-120); *damp = percdamp * mean(diag)
+__global__ void diag_prep_kernel(const float* __restrict__ H, int64_t K, float percdamp,
+                                 float* __restrict__ out_diag, unsigned char* __restrict__ dead,
+                                 float* __restrict__ damp) {
+  __shared__ double part[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < K; i += blockDim.x) {
+    float d = H[i * K + i];
+    const bool is_dead = d == 0.0f;
+    if (is_dead) d = 1.0f;
+    dead[i] = is_dead ? 1 : 0;
+    out_diag[i] = d;
+    s += (double)d;
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) part[threadIdx.x] += part[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float mean = (float)(part[0] / (double)K);
+    *damp = __fmul_rn(percdamp, mean);   // python float * np.float32 -> float32 multiply
+  }
+}
+
+// perm = argsort(diag)[::-1] (gptq.py:125): descending; equal keys keep the order a reversed
+// stable ascending sort gives (larger index first).  One thread per element, O(K) scan each.
+__global__ void rank_perm_kernel(const float* __restrict__ diag, int64_t K, int actorder,
+                                 int32_t* __restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  if (!actorder) { perm[i] = (int32_t)i; return; }
+  const float d = diag[i];
+  int64_t pos = 0;
+  for (int64_t j = 0; j < K; ++j) {
+    const float e = diag[j];
+    pos += (e > d) || (e == d && j > i);
+  }
+  perm[pos] = (int32_t)i;
+}
+
+// Hr[i][j] = Hfix[p(i)][p(j)] (+ damp on the diagonal), p(i) = perm[K-1-i]: the permuted,
+// damped, index-reversed matrix whose upper Cholesky factor is wanted.
+__global__ void gather_reverse_kernel(const float* __restrict__ H, int64_t K,
+                                      const int32_t* __restrict__ perm,
+                                      const float* __restrict__ diag, const float* __restrict__ damp,
+                                      float* __restrict__ Hr) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= K) return;
+  const int64_t pi = perm[K - 1 - i], pj = perm[K - 1 - j];
+  float v = (i == j) ? __fadd_rn(diag[pi], *damp) : H[pi * K + pj];
+  Hr[i * K + j] = v;
+}
+
+// ---- diagonal block: C_jj (upper Cholesky factor, in place) and its inverse ---------------------
+__global__ void __launch_bounds__(256) chol_diag_kernel(float* __restrict__ A, int64_t ld, int64_t j0,
+                                                        int nb, float* __restrict__ DI,
+                                                        int32_t* __restrict__ status) {
+  extern __shared__ float sm[];
+  float* S = sm;                       // [kNB][kPitch] the block, becomes C_jj
+  float* V = sm + kNB * kPitch;        // [kNB][kPitch] its inverse
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < kNB * kNB; idx += 256) {
+    const int r = idx / kNB, c = idx % kNB;
+    float v = (r == c) ? 1.0f : 0.0f;   // identity padding for a short last block
+    if (r < nb && c < nb && c >= r) v = A[(j0 + r) * ld + j0 + c];
+    S[r * kPitch + c] = v;
+    V[r * kPitch + c] = 0.0f;
+  }
+  const int col = tid & (kNB - 1), half = tid >> 7;   // two threads per column, rows interleaved
+  for (int k = 0; k < nb; ++k) {
+    __syncthreads();
+    float piv = S[k * kPitch + k];
+    if (!(piv > 0.0f)) {                // also catches NaN: LAPACK spotrf's `ajj <= 0 || isnan`
+      if (tid == 0) atomicExch(status, 1);
+      piv = 1.0f;
+    }
+    const float d = sqrtf(piv), inv = 1.0f / d;
+    __syncthreads();
+    if (half == 0) {
+      if (col == k) S[k * kPitch + k] = d;
+      else if (col > k) S[k * kPitch + col] *= inv;
+    }
+    __syncthreads();
+    if (col > k) {
+      const float ckc = S[k * kPitch + col];
+      for (int r = k + 1 + half; r <= col; r += 2)
+        S[r * kPitch + col] = fmaf(-S[k * kPitch + r], ckc, S[r * kPitch + col]);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nb * nb; idx += 256) {
+    const int r = idx / nb, c = idx % nb;
+    if (c >= r) A[(j0 + r) * ld + j0 + c] = S[r * kPitch + c];
+  }
+  // V = S^-1 (upper): column c by back substitution, rows aligned across threads so that S[r][k]
+  // is a broadcast and V[k][c] is conflict-free
+  if (half == 0) V[col * kPitch + col] = 1.0f / S[col * kPitch + col];
+  __syncthreads();
+  if (half == 0) {
+    for (int r = kNB - 2; r >= 0; --r) {
+      if (col > r) {
+        float acc = 0.0f;
+        for (int k = r + 1; k <= col; ++k) acc = fmaf(S[r * kPitch + k], V[k * kPitch + col], acc);
+        V[r * kPitch + col] = -acc / S[r * kPitch + r];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < kNB * kNB; idx += 256) {
+    const int r = idx / kNB, c = idx % kNB;
+    DI[idx] = V[r * kPitch + c];
+  }
+}
+
+// VT[j0+r][j0+c] = DI[c][r] (the transposed inverse of a diagonal block, lower triangular)
+__global__ void __launch_bounds__(256) transpose_diag_kernel(const float* __restrict__ DI, int nb,
+                                                             float* __restrict__ VT, int64_t ld,
+                                                             int64_t j0) {
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < nb * nb; idx += gridDim.x * 256) {
+    const int r = idx / nb, c = idx % nb;
+    VT[(j0 + r) * ld + j0 + c] = DI[c * kNB + r];   // 64 KB block, L2-resident
+  }
+}
+
+// U[i][j] = VT[K-1-i][K-1-j] on and above the diagonal, 0 below; identity when the factorization
+// failed (gptq.py:143-150).
+__global__ void reflect_kernel(const float* __restrict__ VT, int64_t K,
+                               const int32_t* __restrict__ status, float* __restrict__ U) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= K) return;
+  float v;
+  if (*status != 0) v = (i == j) ? 1.0f : 0.0f;
+  else v = (j >= i) ? VT[(K - 1 - i) * K + (K - 1 - j)] : 0.0f;
+  U[i * K + j] = v;
+}
+
+struct HinvWorkspace {
+  float* Hr;
+  float* VT;
+  float* DI;
+  float* tmp;
+  float* diag;
+  float* damp;
+  size_t total;
+};
+
+HinvWorkspace carve_hinv(void* base, int64_t K) {
+  HinvWorkspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((char*)base + off) : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t nblk = ceil_div(K, kNB);
+  w.Hr = (float*)take((size_t)K * K * 4);
+  w.VT = (float*)take((size_t)K * K * 4);
+  w.DI = (float*)take((size_t)nblk * kNB * kNB * 4);
+  w.tmp = (float*)take((size_t)kNB * K * 4);
+  w.diag = (float*)take((size_t)K * 4);
+  w.damp = (float*)take(256);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+size_t b200q_hinv_workspace_bytes(int64_t K) {
+  if (K <= 0) return 0;
+  return carve_hinv(nullptr, K).total;
+}
+
+int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int actorder, float* U,
+                              int32_t* perm, unsigned char* dead, int32_t* status, int precision,
+                              void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200Q_REQUIRE(H && U && perm && dead && status && K > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  B200Q_REQUIRE(K < (1ll << 31), B200Q_ERR_UNSUPPORTED, "K must fit in int32");
+  B200Q_REQUIRE(precision == B200Q_TF32 || precision == B200Q_TF32X3 || precision == B200Q_FP32_SIMT,
+                B200Q_ERR_INVALID_ARG, "unknown precision %d", precision);
+  HinvWorkspace ws = carve_hinv(workspace, K);
+  B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
+                "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
+
+  B200Q_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  diag_prep_kernel<<<1, 256, 0, st>>>(H, K, (float)percdamp, ws.diag, dead, ws.damp);
+  B200Q_LAUNCH_OK();
+  rank_perm_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(ws.diag, K, actorder, perm);
+  B200Q_LAUNCH_OK();
+  {
+    dim3 grid((unsigned)ceil_div(K, 256), (unsigned)K);
+    gather_reverse_kernel<<<grid, 256, 0, st>>>(H, K, perm, ws.diag, ws.damp, ws.Hr);
+    B200Q_LAUNCH_OK();
+  }
+  B200Q_CUDA_OK(cudaMemsetAsync(ws.VT, 0, (size_t)K * K * 4, st));
+
+  const size_t diag_smem = (size_t)2 * kNB * kPitch * sizeof(float);
+  B200Q_CUDA_OK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)diag_smem));
+  GemmTN g;
+  // ---- potrf (upper, right-looking) ----
+  for (int64_t j0 = 0, jb = 0; j0 < K; j0 += kNB, ++jb) {
+    const int nb = (int)(K - j0 < kNB ? K - j0 : kNB);
+    float* DIj = ws.DI + jb * kNB * kNB;
+    chol_diag_kernel<<<1, 256, diag_smem, st>>>(ws.Hr, K, j0, nb, DIj, status);
+    B200Q_LAUNCH_OK();
+    const int64_t rest = K - j0 - nb;
+    if (rest <= 0) break;
+    float* P = ws.Hr + j0 * K + j0 + nb;
+    // row panel: P <- C_jj^-T P (through a scratch panel: output rows alias the contraction rows)
+    g = GemmTN{DIj, kNB, P, K, ws.tmp, K, nb, nb, rest, 1.0f, 0, 0, 0, precision};
+    int rc = gemm_tn(g, st);
+    if (rc != B200Q_OK) return rc;
+    B200Q_CUDA_OK(cudaMemcpy2DAsync(P, (size_t)K * 4, ws.tmp, (size_t)K * 4, (size_t)rest * 4, nb,
+                                    cudaMemcpyDeviceToDevice, st));
+    // trailing update, upper triangle only
+    g = GemmTN{P, K, P, K, ws.Hr + (j0 + nb) * K + (j0 + nb), K, nb, rest, rest, -1.0f, 1, 1, 0, precision};
+    rc = gemm_tn(g, st);
+    if (rc != B200Q_OK) return rc;
+  }
+  // ---- trtri: VT = C^-T, row block by row block ----
+  for (int64_t j0 = 0, jb = 0; j0 < K; j0 += kNB, ++jb) {
+    const int nb = (int)(K - j0 < kNB ? K - j0 : kNB);
+    const float* DIj = ws.DI + jb * kNB * kNB;
+    transpose_diag_kernel<<<16, 256, 0, st>>>(DIj, nb, ws.VT, K, j0);
+    B200Q_LAUNCH_OK();
+    if (j0 == 0) continue;
+    g = GemmTN{ws.Hr + j0, K, ws.VT, K, ws.tmp, K, j0, nb, j0, 1.0f, 0, 0, 1, precision};
+    int rc = gemm_tn(g, st);
+    if (rc != B200Q_OK) return rc;
+    g = GemmTN{DIj, kNB, ws.tmp, K, ws.VT + j0 * K, K, nb, nb, j0, -1.0f, 0, 0, 0, precision};
+    rc = gemm_tn(g, st);
+    if (rc != B200Q_OK) return rc;
+  }
+  {
+    dim3 grid((unsigned)ceil_div(K, 256), (unsigned)K);
+    reflect_kernel<<<grid, 256, 0, st>>>(ws.VT, K, status, U);
+    B200Q_LAUNCH_OK();
+  }
+  return B200Q_OK;
+}
+
+}  // extern "C"

@@ -1,5 +1,6 @@
 // rtn.cu — C-ABI entry points of the RTN / MSE / packing path (see include/b200q.h).
 #include "common.cuh"
+#include "dense.cuh"
 #include "minmax.cuh"
 #include "mse_generic.cuh"
 #include "rtn_fused.cuh"
@@ -148,6 +149,40 @@ __global__ void pow_approx_kernel(const float* __restrict__ x, int64_t n, float*
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = pow_norm_approx(fabsf(x[i]));
+}
+
+int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, int64_t group_size,
+                 int symmetric, int reduce_range, double clip_ratio, int mse, float* out_scale,
+                 unsigned char* out_zp, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, symmetric, reduce_range, &qs), B200Q_ERR_INVALID_ARG,
+                "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0);
+  B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
+                "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
+  rc = launch_rowstats(W, s.map, s.rows, ws, st);
+  if (rc != B200Q_OK) return rc;
+  const int blocks = (int)ceil_div(s.rows, 256);
+  if (mse) {
+    B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
+    const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
+    dim3 block(32, kMseCandidates);
+    mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, ws.err);
+    B200Q_LAUNCH_OK();
+    mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
+    B200Q_LAUNCH_OK();
+    mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows, qs,
+                                                out_scale, out_zp, nullptr, kFinalizeGeneric);
+  } else {
+    qparams_from_stats_kernel<<<blocks, 256, 0, st>>>(ws.enc_min, ws.enc_max, s.rows,
+                                                      (float)clip_ratio, qs, out_scale, out_zp);
+  }
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
 }
 
 }  // namespace b200q
