@@ -5,6 +5,7 @@
 #include "mse_generic.cuh"
 #include "rtn_fused.cuh"
 #include "rtn_generic.cuh"
+#include "rtn_stream.cuh"
 
 namespace b200q {
 
@@ -136,6 +137,17 @@ static void launch_fused(const FusedArgs& a, int mode, cudaStream_t st) {
   else rtn_group_fused_kernel<GS, kPlain><<<grid, kFusedThreads, 0, st>>>(a);
 }
 
+// the HBM-bound route: no search, uint4 codes in the MatMulNBits layout (rtn_stream.cuh)
+static void launch_stream_gs(const FusedArgs& a, int64_t gs, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(a.N, kStreamCols), (unsigned)ceil_div(a.G, 2));
+  switch (gs) {
+    case 16: rtn_group_nbits4_kernel<16><<<grid, kStreamThreads, 0, st>>>(a); break;
+    case 32: rtn_group_nbits4_kernel<32><<<grid, kStreamThreads, 0, st>>>(a); break;
+    case 64: rtn_group_nbits4_kernel<64><<<grid, kStreamThreads, 0, st>>>(a); break;
+    default: rtn_group_nbits4_kernel<128><<<grid, kStreamThreads, 0, st>>>(a); break;
+  }
+}
+
 static void launch_fused_gs(const FusedArgs& a, int64_t gs, int mode, cudaStream_t st) {
   switch (gs) {
     case 16: launch_fused<16>(a, mode, st); break;
@@ -242,9 +254,15 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     FusedArgs a;
     a.W = W; a.K = K; a.N = N; a.G = m.G; a.qs = qs; a.clip = clip; a.layout = layout;
     a.out_codes = (unsigned char*)out_codes; a.out_scale = out_scale; a.zp_rows = zp_rows;
+    a.zp_packed = (unsigned char*)out_zp;
     a.masks = ws.masks; a.enc_min = ws.enc_min; a.enc_max = ws.enc_max;
     a.ctl = ws.ctl; a.run_if_state = 0;
     if (!mse) {
+      if (layout == B200Q_MATMUL_NBITS && qs.bits == 4) {
+        launch_stream_gs(a, m.gs, st);   // codes, scales and packed zero points in one launch
+        B200Q_LAUNCH_OK();
+        return B200Q_OK;
+      }
       launch_fused_gs(a, m.gs, kPlain, st);
       B200Q_LAUNCH_OK();
     } else {

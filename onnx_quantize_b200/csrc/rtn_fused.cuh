@@ -85,6 +85,7 @@ struct FusedArgs {
   unsigned char* out_codes;
   float* out_scale;
   unsigned char* zp_rows;   // one byte per parameter row
+  unsigned char* zp_packed; // rtn_stream.cuh: the MatMulNBits zero-point tensor, written directly
   unsigned int* masks;      // kExact: per-row "improved at step i" bit mask
   unsigned int* enc_min;    // kExact: per-row raw min / max (order-preserving encoding), consumed by
   unsigned int* enc_max;    //         the early-stop fix-up (mse_finalize_kernel)

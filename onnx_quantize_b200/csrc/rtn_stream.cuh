@@ -1,0 +1,238 @@
+// rtn_stream.cuh — the HBM-bound kernel of the RTN path: GROUP strategy, no MSE search, uint4 codes
+// written straight in the MatMulNBits layout (BASELINE config 2a).  One read of W, one write of
+// the packed result.  Two earlier versions were measured on B200 (profiles/): the generic fused
+// kernel is issue-bound (29 instructions per element, 40 % of the HBM roofline); a first lean
+// version was L1TEX-bound (95 % L1TEX throughput at 55 % of the roofline) because a warp-level
+// 128-bit load touched eight half-used 128-byte lines.  Hence:
+//   * tile = GS rows x 128 output channels, 256 threads; WARP w owns the GS/8 consecutive rows
+//     [w*GS/8, (w+1)*GS/8) and LANE l the four adjacent columns 4l..4l+3, so every warp-level load
+//     is one fully used 512-byte row segment (4 L1 wavefronts, the minimum) and the nibble pairs
+//     (rows 2j, 2j+1) and 32-bit words of a column's packed block are thread-local;
+//   * min/max with 3-input FMNMX3, folded across the 8 warps through shared memory; scale / zero
+//     point (two IEEE divisions) are computed ONCE per column by thread c of the first 128;
+//   * codes: t = x * (1/s) with packed f32x2 arithmetic, rint through the magic-number add
+//     u = t + (1.5*2^23 + zp), clamp in the magic domain, code = low mantissa bits.  The
+//     reference divides (x / s) and rounds half to even; the reciprocal product can differ from
+//     the quotient in the last bit, so the result is VALIDATED instead of trusted: r = u - magic is
+//     an integer and the exact residual e = fma(r, -s, x) (one rounding) proves
+//     |x/s - r| < 1/2 - delta, which pins rint(RN(x/s)) = r for every element inside the clamp
+//     range (delta covers the rounding of the quotient itself; outside the range both sides clamp).
+//     Chunks that cannot be proven (a tie or near-tie, ~4e-6 of all elements) are redone with the
+//     IEEE division.  Bit-exactness therefore never depends on the approximation, only speed does.
+//   * packed words are staged so that shared-memory traffic is conflict-free both ways (128-bit
+//     stores of four columns' words, 32-bit reads along columns) and every global store is a full
+//     32-byte sector; a CTA walks the two groups whose zero points share a byte, so the
+//     nibble-packed zero-point tensor is written by the same launch.
+#pragma once
+
+#include "common.cuh"
+#include "rtn_fused.cuh"
+
+namespace b200q {
+
+constexpr int kStreamCols = 128;
+constexpr int kStreamThreads = 256;
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int GS>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+rtn_group_nbits4_kernel(const __grid_constant__ FusedArgs a) {
+  static_assert(GS % 16 == 0 && GS <= 128, "group sizes 16..128");
+  constexpr int R = GS / 8;                 // consecutive rows per warp (and thread)
+  constexpr int HR = R < 8 ? R : 8;         // rows per validated chunk
+  constexpr int NH = R / HR;
+  constexpr int BPC = GS / 2;               // packed bytes per column and group
+  constexpr int WPC = BPC / 4;              // 32-bit words per column and group (2..16)
+  __shared__ __align__(16) float red_mn[8][kStreamCols];
+  __shared__ __align__(16) float red_mx[8][kStreamCols];
+  __shared__ __align__(16) float qp_s[kStreamCols];
+  __shared__ __align__(16) int qp_z[kStreamCols];
+  __shared__ __align__(16) unsigned int stage[16][kStreamCols];   // [word of the column block][column]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n0 = (int64_t)blockIdx.x * kStreamCols;
+  const int64_t n = n0 + 4 * lane;
+  const bool col_ok = n < a.N;              // N % 4 == 0 on this path
+  const QSpec qs = a.qs;
+  constexpr float kMagic = 12582912.0f;                       // 1.5 * 2^23: ulp 1, integer in the low bits
+  constexpr float kDelta = 1.9073486328125e-06f;              // 2^-19 > 2^-24 * (|code range| + 2)
+  const float u_lo = kMagic + (float)qs.qmin, u_hi = kMagic + (float)qs.qmax;
+  // A CTA walks the two groups (2*blockIdx.y, +1) whose zero points share one byte of the
+  // MatMulNBits zero-point tensor (qrules/_common.py:96-121: low nibble = even g, an odd count is
+  // padded with 0x8; not packed when there is a single group).
+  unsigned int zp_even = 0;
+
+#pragma unroll 1
+  for (int gi = 0; gi < 2; ++gi) {
+    const int64_t g = 2 * (int64_t)blockIdx.y + gi;
+    if (g >= a.G) break;
+
+    float4 v[R];
+    {
+      const float* base = a.W + ((int64_t)g * GS + (int64_t)R * warp) * a.N + n;
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        v[i] = col_ok ? ldg_stream4(base + (int64_t)i * a.N) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // ---- A2: min / max of this warp's rows, then across the 8 warps ----
+    float mn[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, mx[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+    for (int i = 1; i + 1 < R; i += 2) {
+      mn[0] = fminf(fminf(mn[0], v[i].x), v[i + 1].x); mx[0] = fmaxf(fmaxf(mx[0], v[i].x), v[i + 1].x);
+      mn[1] = fminf(fminf(mn[1], v[i].y), v[i + 1].y); mx[1] = fmaxf(fmaxf(mx[1], v[i].y), v[i + 1].y);
+      mn[2] = fminf(fminf(mn[2], v[i].z), v[i + 1].z); mx[2] = fmaxf(fmaxf(mx[2], v[i].z), v[i + 1].z);
+      mn[3] = fminf(fminf(mn[3], v[i].w), v[i + 1].w); mx[3] = fmaxf(fmaxf(mx[3], v[i].w), v[i + 1].w);
+    }
+    {
+      constexpr int i = R - 1;   // R is even: one row is left over
+      mn[0] = fminf(mn[0], v[i].x); mx[0] = fmaxf(mx[0], v[i].x);
+      mn[1] = fminf(mn[1], v[i].y); mx[1] = fmaxf(mx[1], v[i].y);
+      mn[2] = fminf(mn[2], v[i].z); mx[2] = fmaxf(mx[2], v[i].z);
+      mn[3] = fminf(mn[3], v[i].w); mx[3] = fmaxf(mx[3], v[i].w);
+    }
+    *reinterpret_cast<float4*>(&red_mn[warp][4 * lane]) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+    *reinterpret_cast<float4*>(&red_mx[warp][4 * lane]) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+    __syncthreads();
+
+    // ---- A2 tail + A3: thread c < 128 owns column c ----
+    if (tid < kStreamCols) {
+      float lo = red_mn[0][tid], hi = red_mx[0][tid];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { lo = fminf(lo, red_mn[w][tid]); hi = fmaxf(hi, red_mx[w][tid]); }
+      const QParam p = qparam_from_range(fminf(__fmul_rn(lo, a.clip), 0.0f),
+                                         fmaxf(__fmul_rn(hi, a.clip), 0.0f), qs);
+      qp_s[tid] = p.scale;
+      qp_z[tid] = p.zp;
+      const int64_t col = n0 + tid;
+      if (col < a.N) {
+        a.out_scale[col * a.G + g] = p.scale;
+        const unsigned int z = (unsigned int)p.zp & 0xFu;
+        if (a.G == 1) a.zp_packed[col] = (unsigned char)z;
+        else if (gi == 0 && g + 1 < a.G) zp_even = z;
+        else a.zp_packed[col * ((a.G + 1) / 2) + (g >> 1)] =
+                 (unsigned char)(gi == 0 ? (z | 0x80u) : (zp_even | (z << 4)));
+      }
+    }
+    __syncthreads();
+
+    // ---- A4 + packing ----
+    const float4 s4 = *reinterpret_cast<const float4*>(&qp_s[4 * lane]);
+    const int4 z4 = *reinterpret_cast<const int4*>(&qp_z[4 * lane]);
+    const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+    const int zp[4] = {z4.x, z4.y, z4.z, z4.w};
+    float2 inv01, inv23, c01, c23, ns01, ns23, nc01, nc23;
+    float thr[4];
+    {
+      float inv[4], cc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        inv[c] = rcp_approx(s[c]);
+        cc[c] = kMagic + (float)zp[c];
+        thr[c] = s[c] * (0.5f - kDelta);
+      }
+      inv01 = make_float2(inv[0], inv[1]); inv23 = make_float2(inv[2], inv[3]);
+      c01 = make_float2(cc[0], cc[1]);     c23 = make_float2(cc[2], cc[3]);
+      ns01 = make_float2(-s[0], -s[1]);    ns23 = make_float2(-s[2], -s[3]);
+      nc01 = make_float2(-cc[0], -cc[1]);  nc23 = make_float2(-cc[2], -cc[3]);
+    }
+
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      // t[jj][c]: low byte = packed byte of rows (2jj, 2jj+1) of the chunk, column c.  The low byte
+      // of every magic-domain pattern is the code (0x4B400000 + q, q <= 15), so lo + 16*hi carries
+      // B[n, g, j] = q[2j] | q[2j+1] << 4 (qrules/_common.py:76-87) in its low 8 bits.
+      unsigned int t[HR / 2][4];
+      float res[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int jj = 0; jj < HR / 2; ++jj) {
+        unsigned int lo[4], hi[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float4 x = v[h * HR + 2 * jj + half];
+          const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
+          const float2 u01 = __fadd2_rn(__fmul2_rn(x01, inv01), c01);
+          const float2 u23 = __fadd2_rn(__fmul2_rn(x23, inv23), c23);
+          const float2 r01 = __fadd2_rn(u01, nc01);
+          const float2 r23 = __fadd2_rn(u23, nc23);
+          const float2 e01 = __ffma2_rn(r01, ns01, x01);          // x - r*s, one rounding
+          const float2 e23 = __ffma2_rn(r23, ns23, x23);
+          res[0] = fmaxf(res[0], fabsf(e01.x)); res[1] = fmaxf(res[1], fabsf(e01.y));
+          res[2] = fmaxf(res[2], fabsf(e23.x)); res[3] = fmaxf(res[3], fabsf(e23.y));
+          unsigned int* d = half ? hi : lo;
+          d[0] = __float_as_uint(fminf(fmaxf(u01.x, u_lo), u_hi));
+          d[1] = __float_as_uint(fminf(fmaxf(u01.y, u_lo), u_hi));
+          d[2] = __float_as_uint(fminf(fmaxf(u23.x, u_lo), u_hi));
+          d[3] = __float_as_uint(fminf(fmaxf(u23.y, u_lo), u_hi));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[jj][c] = hi[c] * 16u + lo[c];
+      }
+      const bool proven = res[0] < thr[0] && res[1] < thr[1] && res[2] < thr[2] && res[3] < thr[3];
+      if (!proven) {
+        // a tie / near-tie somewhere in this chunk: the reference's own operation sequence for all
+        // of it (quant_code: IEEE division, round half to even)
+#pragma unroll
+        for (int jj = 0; jj < HR / 2; ++jj) {
+          const float4 x = v[h * HR + 2 * jj], y = v[h * HR + 2 * jj + 1];
+          t[jj][0] = quant_code(x.x, s[0], zp[0], qs.qmin, qs.qmax) + 16 * quant_code(y.x, s[0], zp[0], qs.qmin, qs.qmax);
+          t[jj][1] = quant_code(x.y, s[1], zp[1], qs.qmin, qs.qmax) + 16 * quant_code(y.y, s[1], zp[1], qs.qmin, qs.qmax);
+          t[jj][2] = quant_code(x.z, s[2], zp[2], qs.qmin, qs.qmax) + 16 * quant_code(y.z, s[2], zp[2], qs.qmin, qs.qmax);
+          t[jj][3] = quant_code(x.w, s[3], zp[3], qs.qmin, qs.qmax) + 16 * quant_code(y.w, s[3], zp[3], qs.qmin, qs.qmax);
+        }
+      }
+      if (HR == 8) {
+        // a full chunk is one 32-bit word per column; word index in the column block = 2*warp + h
+        // (R = 16) or warp (R = 8); the four columns' words go out as one 128-bit store
+        unsigned int wd[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const unsigned int w01 = __byte_perm(t[0][c], t[(HR / 2 > 1) ? 1 : 0][c], 0x0040);
+          const unsigned int w23 = __byte_perm(t[(HR / 2 > 2) ? 2 : 0][c], t[(HR / 2 > 3) ? 3 : 0][c], 0x0040);
+          wd[c] = __byte_perm(w01, w23, 0x5410);
+        }
+        *reinterpret_cast<uint4*>(&stage[(R / 8) * warp + h][4 * lane]) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      } else {
+        // R = HR < 8: a warp contributes HR/2 bytes (1 or 2) to a word shared with other warps
+        constexpr int kBytes = HR / 2;
+        const int byte_off = kBytes * warp;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          unsigned char* dst = reinterpret_cast<unsigned char*>(&stage[byte_off >> 2][4 * lane + c]) + (byte_off & 3);
+          if (kBytes == 2) *reinterpret_cast<unsigned short*>(dst) =
+              (unsigned short)__byte_perm(t[0][c], t[(HR / 2 > 1) ? 1 : 0][c], 0x0040);
+          else *dst = (unsigned char)t[0][c];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stores: thread (column, part) writes full 32-byte sectors of the column's block ----
+    {
+      constexpr int kParts = WPC >= 8 ? 2 : 1;              // pieces per column
+      constexpr int kWords = WPC / kParts;                  // words per piece: 8, 4 or 2
+      const int col = tid & (kStreamCols - 1), part = tid >> 7;
+      if (part < kParts && n0 + col < a.N) {
+        unsigned int w[kWords];
+#pragma unroll
+        for (int q = 0; q < kWords; ++q) w[q] = stage[part * kWords + q][col];
+        unsigned char* dst = a.out_codes + (n0 + col) * (a.K / 2) + g * BPC + part * kWords * 4;
+        if (kWords >= 4) {
+#pragma unroll
+          for (int q = 0; q + 3 < kWords; q += 4)
+            *reinterpret_cast<uint4*>(dst + 4 * q) = make_uint4(w[q], w[q + 1], w[q + 2], w[q + 3]);
+        } else {
+          *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[kWords > 1 ? 1 : 0]);
+        }
+      }
+    }
+    __syncthreads();   // staging and reduction buffers are reused by the second group
+  }
+}
+
+}  // namespace b200q

@@ -128,3 +128,31 @@ def test_early_stop_info(cuda):
             assert np.array_equal(q.cpu().numpy().view(np.int8), qo)
             lo, hi, trace = O.mse_min_max(O.to_rows(w, strategy), "int8", strategy, True, False, return_trace=True)
             assert int(info.cpu()[0]) == len(trace) - 1
+
+
+@pytest.mark.parametrize("gs", [16, 32, 64, 128])
+@pytest.mark.parametrize("sym,rr,clip", [(False, False, 1.0), (False, False, 0.9), (True, False, 0.95),
+                                         (False, True, 1.0)])
+def test_stream_kernel_matmul_nbits_bit_exact(cuda, gs, sym, rr, clip):
+    """The HBM-bound kernel (rtn_stream.cuh: reciprocal multiply validated by an exact residual,
+    zero points packed in the same launch) against the oracle, byte for byte: ragged tiles, odd
+    group counts, a single group, and inputs made of exact rounding ties."""
+    from onnx_quantize_b200 import device_api as D
+    rng = np.random.default_rng(gs * 7 + int(sym) + 2 * int(rr))
+    for (k, n) in [(gs, 48), (3 * gs, 80), (4 * gs, 1024), (8 * gs, 4096 + 16), (5 * gs, 16)]:
+        w = (rng.standard_normal((k, n)) * 0.02).astype(np.float32)
+        w[rng.integers(0, k, 16), rng.integers(0, n, 16)] *= 25
+        # half of the columns: values on the quantization grid's midpoints (x/s = m + 0.5 exactly
+        # representable), which must round half to even like np.round
+        step = np.float32(2.0 ** -7)
+        ties = (rng.integers(-15, 16, (k, n // 2)).astype(np.float32) + 0.5) * step / 2
+        ties[0, :] = 15 * step / 2
+        ties[1, :] = -15 * step / 2
+        w[:, : n // 2] = ties
+        wt = torch.from_numpy(w).to(cuda)
+        b, s, z = D.rtn_quantize(wt, "uint4", "group", gs, sym, rr, clip, False, layout="matmul_nbits")
+        qo, so, zo = O.rtn_quantize(w, "uint4", "group", gs, sym, rr, clip, False)
+        ob, os_, oz = O.matmul_nbits_layout(qo, so, zo, gs, 4)
+        assert np.array_equal(b.cpu().numpy(), ob), (k, n)
+        assert np.array_equal(bits(s.cpu().numpy()), bits(os_)), (k, n)
+        assert z.shape == oz.shape and np.array_equal(z.cpu().numpy(), oz), (k, n)
