@@ -53,6 +53,10 @@ def parse():
     p.add_argument("--layers", type=int, default=N_LAYERS, help="model depth (debug only)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-gptq", action="store_true")
+    p.add_argument("--gptq-layers", type=int, default=4,
+                   help="Llama-3-8B-shaped layers in the GPTQ sample (the model has 32)")
+    p.add_argument("--gptq-precision", default="tf32x3", choices=["tf32", "tf32x3"])
     return p.parse_args()
 
 
@@ -154,6 +158,109 @@ def make_weights(torch, device, layers, rank):
     return ws
 
 
+# ------------------------------------------------------------------------------------------------
+# GPTQ variant (BASELINE config 5): INT4 g128 on Llama-3-8B-shaped layers, 128 x 2048 calibration
+# tokens, calibration tokens split over the ranks (NCCL sum-reduce of every Hessian to the rank that
+# owns its solve), solves sharded over the ranks.  Strong scaling: the sample is fixed.
+# ------------------------------------------------------------------------------------------------
+GPTQ_GROUPS = [("qkv", 4096, [(4096, 4096), (4096, 1024), (4096, 1024)]), ("o", 4096, [(4096, 4096)]),
+               ("gate_up", 4096, [(4096, 14336), (4096, 14336)]), ("down", 14336, [(14336, 4096)])]
+GPTQ_SAMPLES, GPTQ_SEQ = 128, 2048
+
+
+def run_gptq_variant(args, torch, dist, device, world, rank):
+    from onnx_quantize_b200 import gptq_device as G
+    from onnx_quantize_b200.core._dtypes import QuantType
+    from onnx_quantize_b200.hessian import hessian_accumulate
+    from onnx_quantize_b200.parallel.shard import assign_units
+
+    layers = args.gptq_layers
+    tokens = GPTQ_SAMPLES * GPTQ_SEQ
+    t_local = tokens // world
+    gen = torch.Generator(device=device)
+    gen.manual_seed(4242 + rank)
+    xs = {k: torch.randn((t_local, k), generator=gen, device=device, dtype=torch.float32) for k in (4096, 14336)}
+    ws = {}
+    for _, _, shapes in GPTQ_GROUPS:
+        for shp in shapes:
+            if shp not in ws:
+                ws[shp] = torch.randn(shp, generator=gen, device=device, dtype=torch.float32) * 0.02
+    units = [(l, gi) for l in range(layers) for gi in range(len(GPTQ_GROUPS))]
+    costs = [GPTQ_GROUPS[gi][1] ** 3 * 2.0 / 3 + sum(k * k * n for k, n in GPTQ_GROUPS[gi][2]) for _, gi in units]
+    plan = assign_units(costs, world)
+    owner = {}
+    for r, idxs in enumerate(plan):
+        for i in idxs:
+            owner[units[i]] = r
+    alpha = 2.0 / GPTQ_SAMPLES
+    hs = {}
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def one_step():
+        e0 = ev()
+        for u in units:                                    # G1: every rank, its share of the tokens
+            k = GPTQ_GROUPS[u[1]][1]
+            h = hs.get(u)
+            if h is None:
+                h = hs[u] = torch.empty((k, k), dtype=torch.float32, device=device)
+            hessian_accumulate(xs[k], h, alpha=alpha, beta=0.0, precision=args.gptq_precision)
+        e1 = ev()
+        if world > 1:                                      # the exchange step: sum to the owner
+            for u in units:
+                dist.reduce(hs[u], dst=owner[u], op=dist.ReduceOp.SUM)
+        e2 = ev()
+        for u in units:                                    # G2-G4 on the owner
+            if owner[u] != rank:
+                continue
+            f = G.hinv_cholesky_upper(hs[u], 0.01, False, args.gptq_precision)
+            for shp in GPTQ_GROUPS[u[1]][2]:
+                G.gptq_quantize(ws[shp], f, QuantType.QInt4, "group", 128, True, False, 1.0, False, 128,
+                                "propagate", args.gptq_precision)
+        e3 = ev()
+        return e0, e1, e2, e3
+
+    one_step()                                             # warm-up (workspaces, attributes)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1, e2, e3 = one_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e3), e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)],
+                     device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, hess_ms, red_ms, solve_ms = (float(v) for v in t)
+    flops = sum(2.0 * tokens * GPTQ_GROUPS[gi][1] ** 2 for _, gi in units)     # de-duplicated by input
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    bf16 = float(peaks.get("bf16_tflops_sustained", 1393.9))
+    tf = flops / (hess_ms * 1e-3) / 1e12
+    return {
+        "workload": f"cfg5: GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
+                    f"Llama-3-8B-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
+                    f"{GPTQ_SAMPLES}x{GPTQ_SEQ} calibration tokens split over {world} rank(s)",
+        "precision": args.gptq_precision, "scaling": "strong", "n_gpus": world,
+        "s_per_step": total_ms * 1e-3, "s_per_model_extrapolated": total_ms * 1e-3 * 32 / layers,
+        "extrapolation": f"x{32 / layers:g}: the 32 layers are identical in shape",
+        "hessian_s": hess_ms * 1e-3, "hessian_reduce_s": red_ms * 1e-3, "solve_s": solve_ms * 1e-3,
+        "roofline": {"bound": "tensor", "kernel": "hessian_kernel", "achieved": tf, "unit": "TFLOP/s",
+                     "peak": bf16 / 2, "frac": tf / (bf16 / 2),
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 "
+                                    "rate; 3xTF32 issues three MMAs per product, so its ceiling is 1/3 of this)",
+                     "flops": flops},
+    }
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -247,6 +354,13 @@ def run_gpu_arm(args):
                "ms_per_step": e2e_s * 1e3,
                "api": "onnx_quantize_b200.pipeline.quantize_weights_bulk (pinned host weights in, host results out)"}
 
+    gptq = None
+    if not args.no_gptq:
+        del plans, weights
+        D.dev.release_workspaces()
+        torch.cuda.empty_cache()
+        gptq = run_gptq_variant(args, torch, dist, device, world, rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -267,17 +381,27 @@ def run_gpu_arm(args):
                    "parallelism": f"{world} rank(s), one model-sized set each, no collective",
                    "cache": "inputs (27.9 GB) larger than L2; no flush needed"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": {"per_launch_bytes": 243.74e6, "algorithmic_bytes_same_launch": 266.3e6 * 4.0 / 4.535,
+                                 "note": "dram__bytes_read+write of one 4096x14336 launch (ncu --set full, "
+                                         "profiles/r1_prof_rtn_details.txt): 235.2 MB read = the f32 weight once, "
+                                         "8.5 MB written (the rest of the 29 MB result is still in L2 at kernel end)"},
+                     "peak_source": peak_src,
                      "kernel": "rtn_group_fused_kernel<128,MSE>",
                      "note": "the MSE search is FP32/FP64-issue bound (20 candidates per element); "
                              "the HBM-bound kernel is variants.cfg2a_no_mse"},
-        "variants": {"cfg2a_no_mse_clip0.9": {"ms_per_step": ms_plain,
-                                             "value": in_bytes / (ms_plain * 1e-3) / 1e9, "unit": "GB/s",
-                                             "roofline_frac": achieved_plain / peak}},
+        "variants": {"cfg2a_no_mse_clip0.9": {
+            "ms_per_step": ms_plain, "value": world * in_bytes / (ms_plain * 1e-3) / 1e9, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "rtn_group_nbits4_kernel<128>", "achieved": achieved_plain,
+                         "peak": peak, "unit": "GB/s", "frac": achieved_plain / peak,
+                         "traffic": {"per_launch_bytes": 244.14e6,
+                                     "note": "one 4096x14336 launch, profiles/r1_stream_v2_raw.csv"}}}},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_mse * 1e3,
         "clocks": sampler.summary() if sampler else None,
     }
+    if gptq:
+        line["variants"]["gptq_int4_g128"] = gptq
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -1,0 +1,117 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo process groups (the N>1 path of SURVEY.md §8e).
+The collectives are backend-agnostic; on the GPU box the same functions run over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from onnx_quantize_b200.parallel import calibration as C
+from onnx_quantize_b200.parallel import shard as S
+from oracle import np_oracle as O
+
+LLAMA_LAYER = [(4096, 4096), (4096, 1024), (4096, 1024), (4096, 4096), (4096, 14336), (4096, 14336),
+               (14336, 4096)]
+
+
+def test_assign_units_balances_the_llama_set():
+    costs = [k * n for _ in range(32) for (k, n) in LLAMA_LAYER]
+    for ranks in (1, 2, 4, 8):
+        plan = S.assign_units(costs, ranks)
+        assert sorted(i for p in plan for i in p) == list(range(len(costs)))
+        assert S.imbalance(costs, plan) < 0.02
+    assert S.assign_units(costs, 8) == S.assign_units(costs, 8)       # deterministic
+    assert S.assign_units([], 3) == [[], [], []]
+    assert S.assign_units([5.0], 4)[0] == [0]
+
+
+def test_shard_batches_round_robin():
+    assert C.shard_batches(10, 0, 4) == [0, 4, 8] and C.shard_batches(10, 3, 4) == [3, 7]
+    assert sorted(sum((C.shard_batches(10, r, 4) for r in range(4)), [])) == list(range(10))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)     # same stream on every rank
+        n_batches, n_tensors, k = 7, 3, 24
+        acts = rng.standard_normal((n_batches, n_tensors, 5, 11)).astype(np.float32)
+        xs = rng.standard_normal((n_batches, 4, 6, k)).astype(np.float32)
+        mine = C.shard_batches(n_batches)
+
+        # ---- activation ranges, momentum 0: one MIN all-reduce --------------------------------
+        local = torch.tensor([[acts[mine, t].min(), acts[mine, t].max()] for t in range(n_tensors)])
+        got = C.allreduce_minmax(local.clone())
+        want = torch.tensor([[acts[:, t].min(), acts[:, t].max()] for t in range(n_tensors)])
+        assert torch.equal(got, want)
+
+        # ---- momentum > 0: gather per-batch pairs, replay in global order ----------------------
+        pairs = torch.tensor([[[acts[b, t].min(), acts[b, t].max()] for t in range(n_tensors)] for b in mine])
+        allp = C.gather_batch_pairs(pairs, n_batches)
+        assert allp.shape == (n_batches, n_tensors, 2)
+        for m in (0.0, 0.9):
+            state = C.replay_ema(allp, m).numpy()
+            for t in range(n_tensors):
+                ref = O.MinMax(momentum=m)
+                for b in range(n_batches):
+                    ref.collect("x", acts[b, t])
+                assert np.float32(ref.stats["x"][0]) == state[t, 0] and np.float32(ref.stats["x"][1]) == state[t, 1]
+
+        # ---- Hessian: weighted SUM all-reduce equals the single-process accumulation ----------
+        h = np.zeros((k, k), np.float32)
+        n = 0
+        for b in mine:
+            h, n = O.accumulate_hessian(xs[b], h, n)
+        ht, n_total = C.allreduce_hessian(torch.from_numpy(h.copy()), n)
+        h_ref = np.zeros((k, k), np.float32)
+        n_ref = 0
+        for b in range(n_batches):
+            h_ref, n_ref = O.accumulate_hessian(xs[b], h_ref, n_ref)
+        assert n_total == n_ref
+        assert np.abs(ht.numpy() - h_ref).max() / np.abs(h_ref).max() < 1e-6
+        # reduce-to-owner variant
+        hd, _ = C.allreduce_hessian(torch.from_numpy(h.copy()), n, dst=1)
+        if rank == 1:
+            assert np.abs(hd.numpy() - h_ref).max() / np.abs(h_ref).max() < 1e-6
+
+        # ---- gather of sharded results -------------------------------------------------------
+        names = [f"w{i}" for i in range(5)]
+        costs = [3, 9, 1, 7, 5]
+        plan = S.assign_units(costs, world)
+        local_res = {names[i]: (np.full(2, i), np.float32(i), np.int8(i)) for i in plan[rank]}
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(local_res, gathered, dst=0)
+        if rank == 0:
+            merged = {}
+            for part in gathered:
+                merged.update(part)
+            assert sorted(merged) == names and all(int(merged[n][1]) == int(n[1:]) for n in names)
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_collectives():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
