@@ -237,6 +237,13 @@ def run_gptq_variant(args, torch, dist, device, world, rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, hess_ms, red_ms, solve_ms = (float(v) for v in t)
     flops = sum(2.0 * tokens * GPTQ_GROUPS[gi][1] ** 2 for _, gi in units)     # de-duplicated by input
+
+    def executed(k):   # the kernel only computes the 128x256 tiles that touch the upper triangle
+        n_ib, n_jb = -(-k // 128), -(-k // 256)
+        tiles = sum(max(n_jb - (ib * 128) // 256, 0) for ib in range(n_ib))
+        return 2.0 * tokens * tiles * 128 * 256 * (3 if args.gptq_precision == "tf32x3" else 1)
+
+    mma_flops = sum(executed(GPTQ_GROUPS[gi][1]) for _, gi in units)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -244,7 +251,7 @@ def run_gptq_variant(args, torch, dist, device, world, rank):
     except Exception:  # noqa: BLE001
         pass
     bf16 = float(peaks.get("bf16_tflops_sustained", 1393.9))
-    tf = flops / (hess_ms * 1e-3) / 1e12
+    tf = mma_flops / world / (hess_ms * 1e-3) / 1e12       # per GPU: every rank contracts tokens/world
     return {
         "workload": f"cfg5: GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
                     f"Llama-3-8B-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
@@ -253,10 +260,12 @@ def run_gptq_variant(args, torch, dist, device, world, rank):
         "s_per_step": total_ms * 1e-3, "s_per_model_extrapolated": total_ms * 1e-3 * 32 / layers,
         "extrapolation": f"x{32 / layers:g}: the 32 layers are identical in shape",
         "hessian_s": hess_ms * 1e-3, "hessian_reduce_s": red_ms * 1e-3, "solve_s": solve_ms * 1e-3,
+        "hessian_tflops_algorithmic": flops / (hess_ms * 1e-3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "hessian_kernel", "achieved": tf, "unit": "TFLOP/s",
                      "peak": bf16 / 2, "frac": tf / (bf16 / 2),
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 "
-                                    "rate; 3xTF32 issues three MMAs per product, so its ceiling is 1/3 of this)",
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the "
+                                    "bf16 rate); achieved = tf32 MMA flops actually issued per GPU (upper-triangle "
+                                    "tiles only, x3 products in 3xTF32 mode) / Hessian time",
                      "flops": flops},
     }
 
