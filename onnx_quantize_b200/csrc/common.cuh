@@ -79,10 +79,14 @@ __device__ __forceinline__ QParam qparam_from_range(float mn, float mx, const QS
   if (qs.symmetric) {
     // utils.py:296-298 then :273-294 — the division is carried out in float64 because
     // `max_levels` is an np.float64 scalar (strong type under NEP-50), then cast to f32.
-    float a = fmaxf(fabsf(mn), fabsf(mx));
-    double s = (double)a / qs.sym_levels;
-    if (s < (double)FLT_MIN) s = 1.0;
-    p.scale = (float)s;
+    // The float64 quotient rounded to float32 equals the IEEE float32 quotient: double rounding is
+    // innocuous for division when the wide format has >= 2*24+2 significand bits (53 here), and
+    // `a/L < FLT_MIN` (decided on the float64 quotient) is `a < FLT_MIN*L` exactly (L <= 127, the
+    // product is representable; a float32 `a` cannot sit within 2^-53 relative of the threshold
+    // without being on it).  So no float64 arithmetic is needed on the device.
+    const float a = fmaxf(fabsf(mn), fabsf(mx));
+    const float L = (float)qs.sym_levels;
+    p.scale = (a < __fmul_rn(FLT_MIN, L)) ? 1.0f : __fdiv_rn(a, L);
     p.zp = qs.sym_zero;
   } else {
     // utils.py:258-271 — float32 throughout (python-int divisor is a weak scalar)

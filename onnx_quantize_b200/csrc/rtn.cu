@@ -5,6 +5,7 @@
 #include "mse_generic.cuh"
 #include "rtn_fused.cuh"
 #include "rtn_generic.cuh"
+#include "rtn_mse4.cuh"
 #include "rtn_stream.cuh"
 
 namespace b200q {
@@ -132,7 +133,8 @@ static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWor
 template <int GS>
 static void launch_fused(const FusedArgs& a, int mode, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(a.N, kFusedCols), (unsigned)a.G);
-  if (mode == kTwoTier) rtn_group_fused_kernel<GS, kTwoTier><<<grid, kFusedThreads, 0, st>>>(a);
+  if (mode == kTwoTier && a.qs.bits == 4) rtn_group_mse4_kernel<GS><<<grid, kFusedThreads, 0, st>>>(a);
+  else if (mode == kTwoTier) rtn_group_fused_kernel<GS, kTwoTier><<<grid, kFusedThreads, 0, st>>>(a);
   else if (mode == kExact) rtn_group_fused_kernel<GS, kExact><<<grid, kFusedThreads, 0, st>>>(a);
   else rtn_group_fused_kernel<GS, kPlain><<<grid, kFusedThreads, 0, st>>>(a);
 }

@@ -123,6 +123,117 @@ __device__ __forceinline__ float exact_err(float v, const QParam& c, const QSpec
   return pow_norm(fabsf(d));
 }
 
+// ---- per-row outputs, A4 and packing of one GS x 64 tile (shared by the fused kernels) ----------
+template <int GS>
+__device__ __forceinline__ void fused_store(const FusedArgs& a, const float (&x)[GS / 8][4],
+                                            const QParam (&qp)[4], unsigned char* stage, int tid,
+                                            int rl, int cq_cta, int64_t n0, int64_t n, int64_t g,
+                                            bool col_ok) {
+  constexpr int M = GS / 8;
+  const QSpec qs = a.qs;
+  // ---- per-row outputs ----
+  if (rl == 0 && col_ok) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int64_t row = (n + c) * a.G + g;
+      a.out_scale[row] = qp[c].scale;
+      a.zp_rows[row] = encode_code(qp[c].zp, qs);
+    }
+  }
+
+  // ---- A4 + packing, staged through shared memory for full-width stores ----
+  unsigned int q4[M];   // 4 codes (one byte each) per owned row
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    unsigned int w = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int q = quant_code(x[m][c], qp[c].scale, qp[c].zp, qs.qmin, qs.qmax);
+      w |= (unsigned int)encode_code(q, qs) << (8 * c);
+    }
+    q4[m] = w;
+  }
+
+  if (a.layout == B200Q_KN_BYTES) {
+    // stage[row][80]: word (row*20 + cq_cta); 20*rl mod 32 = {0,20,8,28,16,4,24,12}, + cq (0..3)
+    // -> conflict-free for the 8 row lanes x 4 quads of a warp
+    unsigned int* s32 = reinterpret_cast<unsigned int*>(stage);
+#pragma unroll
+    for (int m = 0; m < M; ++m) s32[(rl + 8 * m) * 20 + cq_cta] = q4[m];
+    __syncthreads();
+    for (int idx = tid; idx < GS * 4; idx += kFusedThreads) {
+      int row = idx >> 2, seg = idx & 3;
+      if (n0 + seg * 16 < a.N) {
+        uint4 v = *reinterpret_cast<const uint4*>(stage + row * 80 + seg * 16);
+        *reinterpret_cast<uint4*>(a.out_codes + ((int64_t)g * GS + row) * a.N + n0 + seg * 16) = v;
+      }
+    }
+  } else if (a.layout == B200Q_PACKED_FLAT) {
+    // layout A: pairs are adjacent in N.  stage[row][36], two bytes per thread and row
+    unsigned short* s16 = reinterpret_cast<unsigned short*>(stage);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      unsigned int w = q4[m];
+      unsigned int b0 = (w & 0xFu) | ((w >> 4) & 0xF0u);
+      unsigned int b1 = ((w >> 16) & 0xFu) | ((w >> 20) & 0xF0u);
+      s16[(rl + 8 * m) * 18 + cq_cta] = (unsigned short)(b0 | (b1 << 8));
+    }
+    __syncthreads();
+    for (int idx = tid; idx < GS * 8; idx += kFusedThreads) {
+      int row = idx >> 3, wd = idx & 7;
+      if (n0 + wd * 8 < a.N) {
+        unsigned int v = *reinterpret_cast<const unsigned int*>(stage + row * 36 + wd * 4);
+        *reinterpret_cast<unsigned int*>(a.out_codes + (((int64_t)g * GS + row) * a.N + n0) / 2 +
+                                         wd * 4) = v;
+      }
+    }
+  } else if (qs.bits == 4) {
+    // layout B, 4-bit: B[n, g, j] = q[2j] | q[2j+1] << 4 along K.  Row lanes 2t / 2t+1 exchange
+    // their codes; the even lane emits columns 0,1 of the quad, the odd lane columns 2,3.
+    const bool odd = rl & 1;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      unsigned int mine = q4[m];
+      unsigned int other = __shfl_xor_sync(0xffffffffu, mine, 1);
+      unsigned int lo = odd ? other : mine, hi = odd ? mine : other;   // lo = even row 2j
+      int cbase = odd ? 2 : 0;
+      int j = (rl >> 1) + 4 * m;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        int c = cbase + cc;
+        unsigned int b = ((lo >> (8 * c)) & 0xFu) | (((hi >> (8 * c)) & 0xFu) << 4);
+        stage[(4 * cq_cta + c) * 68 + j] = (unsigned char)b;
+      }
+    }
+    __syncthreads();
+    constexpr int WPC = GS / 8;   // 32-bit words per column
+    for (int idx = tid; idx < kFusedCols * WPC; idx += kFusedThreads) {
+      int col = idx / WPC, wd = idx - col * WPC;
+      if (n0 + col < a.N) {
+        unsigned int v = *reinterpret_cast<const unsigned int*>(stage + col * 68 + wd * 4);
+        *reinterpret_cast<unsigned int*>(a.out_codes + (n0 + col) * (a.K / 2) + g * (GS / 2) +
+                                         wd * 4) = v;
+      }
+    }
+  } else {
+    // layout B, 8-bit: (N, G, gs) = transpose of the tile
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        stage[(4 * cq_cta + c) * (GS + 4) + rl + 8 * m] = (unsigned char)((q4[m] >> (8 * c)) & 0xFF);
+    __syncthreads();
+    constexpr int WPC = GS / 4;
+    for (int idx = tid; idx < kFusedCols * WPC; idx += kFusedThreads) {
+      int col = idx / WPC, wd = idx - col * WPC;
+      if (n0 + col < a.N) {
+        unsigned int v = *reinterpret_cast<const unsigned int*>(stage + col * (GS + 4) + wd * 4);
+        *reinterpret_cast<unsigned int*>(a.out_codes + (n0 + col) * a.K + g * GS + wd * 4) = v;
+      }
+    }
+  }
+}
+
 template <int GS, int MODE>
 __global__ void __launch_bounds__(kFusedThreads, MODE == kPlain ? 4 : 3)
 rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
@@ -322,107 +433,7 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
     }
   }
 
-  // ---- per-row outputs ----
-  if (rl == 0 && col_ok) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      int64_t row = (n + c) * a.G + g;
-      a.out_scale[row] = qp[c].scale;
-      a.zp_rows[row] = encode_code(qp[c].zp, qs);
-    }
-  }
-
-  // ---- A4 + packing, staged through shared memory for full-width stores ----
-  unsigned int q4[M];   // 4 codes (one byte each) per owned row
-#pragma unroll
-  for (int m = 0; m < M; ++m) {
-    unsigned int w = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      int q = quant_code(x[m][c], qp[c].scale, qp[c].zp, qs.qmin, qs.qmax);
-      w |= (unsigned int)encode_code(q, qs) << (8 * c);
-    }
-    q4[m] = w;
-  }
-
-  if (a.layout == B200Q_KN_BYTES) {
-    // stage[row][80]: word (row*20 + cq_cta); 20*rl mod 32 = {0,20,8,28,16,4,24,12}, + cq (0..3)
-    // -> conflict-free for the 8 row lanes x 4 quads of a warp
-    unsigned int* s32 = reinterpret_cast<unsigned int*>(stage);
-#pragma unroll
-    for (int m = 0; m < M; ++m) s32[(rl + 8 * m) * 20 + cq_cta] = q4[m];
-    __syncthreads();
-    for (int idx = tid; idx < GS * 4; idx += kFusedThreads) {
-      int row = idx >> 2, seg = idx & 3;
-      if (n0 + seg * 16 < a.N) {
-        uint4 v = *reinterpret_cast<const uint4*>(stage + row * 80 + seg * 16);
-        *reinterpret_cast<uint4*>(a.out_codes + ((int64_t)g * GS + row) * a.N + n0 + seg * 16) = v;
-      }
-    }
-  } else if (a.layout == B200Q_PACKED_FLAT) {
-    // layout A: pairs are adjacent in N.  stage[row][36], two bytes per thread and row
-    unsigned short* s16 = reinterpret_cast<unsigned short*>(stage);
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-      unsigned int w = q4[m];
-      unsigned int b0 = (w & 0xFu) | ((w >> 4) & 0xF0u);
-      unsigned int b1 = ((w >> 16) & 0xFu) | ((w >> 20) & 0xF0u);
-      s16[(rl + 8 * m) * 18 + cq_cta] = (unsigned short)(b0 | (b1 << 8));
-    }
-    __syncthreads();
-    for (int idx = tid; idx < GS * 8; idx += kFusedThreads) {
-      int row = idx >> 3, wd = idx & 7;
-      if (n0 + wd * 8 < a.N) {
-        unsigned int v = *reinterpret_cast<const unsigned int*>(stage + row * 36 + wd * 4);
-        *reinterpret_cast<unsigned int*>(a.out_codes + (((int64_t)g * GS + row) * a.N + n0) / 2 +
-                                         wd * 4) = v;
-      }
-    }
-  } else if (qs.bits == 4) {
-    // layout B, 4-bit: B[n, g, j] = q[2j] | q[2j+1] << 4 along K.  Row lanes 2t / 2t+1 exchange
-    // their codes; the even lane emits columns 0,1 of the quad, the odd lane columns 2,3.
-    const bool odd = rl & 1;
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-      unsigned int mine = q4[m];
-      unsigned int other = __shfl_xor_sync(0xffffffffu, mine, 1);
-      unsigned int lo = odd ? other : mine, hi = odd ? mine : other;   // lo = even row 2j
-      int cbase = odd ? 2 : 0;
-      int j = (rl >> 1) + 4 * m;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        int c = cbase + cc;
-        unsigned int b = ((lo >> (8 * c)) & 0xFu) | (((hi >> (8 * c)) & 0xFu) << 4);
-        stage[(4 * cq_cta + c) * 68 + j] = (unsigned char)b;
-      }
-    }
-    __syncthreads();
-    constexpr int WPC = GS / 8;   // 32-bit words per column
-    for (int idx = tid; idx < kFusedCols * WPC; idx += kFusedThreads) {
-      int col = idx / WPC, wd = idx - col * WPC;
-      if (n0 + col < a.N) {
-        unsigned int v = *reinterpret_cast<const unsigned int*>(stage + col * 68 + wd * 4);
-        *reinterpret_cast<unsigned int*>(a.out_codes + (n0 + col) * (a.K / 2) + g * (GS / 2) +
-                                         wd * 4) = v;
-      }
-    }
-  } else {
-    // layout B, 8-bit: (N, G, gs) = transpose of the tile
-#pragma unroll
-    for (int m = 0; m < M; ++m)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        stage[(4 * cq_cta + c) * (GS + 4) + rl + 8 * m] = (unsigned char)((q4[m] >> (8 * c)) & 0xFF);
-    __syncthreads();
-    constexpr int WPC = GS / 4;
-    for (int idx = tid; idx < kFusedCols * WPC; idx += kFusedThreads) {
-      int col = idx / WPC, wd = idx - col * WPC;
-      if (n0 + col < a.N) {
-        unsigned int v = *reinterpret_cast<const unsigned int*>(stage + col * (GS + 4) + wd * 4);
-        *reinterpret_cast<unsigned int*>(a.out_codes + (n0 + col) * a.K + g * GS + wd * 4) = v;
-      }
-    }
-  }
+  fused_store<GS>(a, x, qp, stage, tid, rl, cq_cta, n0, n, g, col_ok);
 }
 
 }  // namespace b200q
