@@ -270,6 +270,71 @@ def run_gptq_variant(args, torch, dist, device, world, rank):
     }
 
 
+# ------------------------------------------------------------------------------------------------
+# cfg1 / cfg3 variants: the other two HBM-bound kernels of the path
+# ------------------------------------------------------------------------------------------------
+def run_small_variants(torch, device, peak):
+    from onnx_quantize_b200 import device_api as D
+    from onnx_quantize_b200.core._dtypes import QuantType
+
+    def time_ms(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    out = {}
+    # cfg1: RTN int8 symmetric per-tensor, two 4096x4096 weights (64 MiB each: L2-resident second pass)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(0)
+    ws = [torch.randn((4096, 4096), generator=gen, device=device) * 0.02 for _ in range(2)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > L2 (126 MB)
+
+    def cfg1():
+        for w in ws:
+            D.rtn_quantize(w, QuantType.QInt8, "tensor", -1, True, False, 1.0, False)
+
+    ms = time_ms(cfg1)
+    elts = sum(w.numel() for w in ws)
+    out["cfg1_int8_sym_tensor"] = {
+        "workload": "cfg1: RTN int8 symmetric per-tensor, 2 x (4096x4096) f32 (codes one byte per element)",
+        "ms_per_step": ms, "value": 4 * elts / (ms * 1e-3) / 1e9, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "minmax_partials_kernel + quantize_rows_kernel",
+                     "achieved": 5.0 * elts / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": 5.0 * elts / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_element": 5.0,
+                     "note": "two passes over W (global min/max must precede any code); the second pass "
+                             "re-reads the 64 MiB weight from L2"}}
+    # cfg3: static-calibration min/max of 100 x 512 x 4096 activations in 10 batches, then A3
+    acts = [torch.randn((10, 512, 4096), generator=gen, device=device) for _ in range(10)]
+    pairs = torch.empty((10, 2), dtype=torch.float32, device=device)
+    state = torch.zeros((2,), dtype=torch.float32, device=device)
+    valid = torch.zeros((1,), dtype=torch.int32, device=device)
+
+    def cfg3():
+        valid.zero_()
+        for i, x in enumerate(acts):
+            D.minmax_reduce(x.reshape(-1), pairs[i])
+        D.minmax_merge(state, valid, pairs, 0.0)
+        D.qparams(state[0:1].clamp(max=0), state[1:2].clamp(min=0), QuantType.QUInt8)
+
+    ms = time_ms(cfg3, iters=5)
+    elts = sum(x.numel() for x in acts)
+    out["cfg3_activation_minmax"] = {
+        "workload": "cfg3: MinMax calibration of one tensor, 100x512x4096 f32 activations in 10 batches + uint8 scale/zp",
+        "ms_per_step": ms, "value": 4 * elts / (ms * 1e-3) / 1e9, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "minmax_partials_kernel", "achieved": 4.0 * elts / (ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": 4.0 * elts / (ms * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_element": 4.0}}
+    del flush
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -363,6 +428,7 @@ def run_gpu_arm(args):
                "ms_per_step": e2e_s * 1e3,
                "api": "onnx_quantize_b200.pipeline.quantize_weights_bulk (pinned host weights in, host results out)"}
 
+    small = run_small_variants(torch, device, measured_peaks()[0]) if rank == 0 else None
     gptq = None
     if not args.no_gptq:
         del plans, weights
@@ -409,6 +475,8 @@ def run_gpu_arm(args):
         "wall_ms_per_step": wall_mse * 1e3,
         "clocks": sampler.summary() if sampler else None,
     }
+    if small:
+        line["variants"].update(small)
     if gptq:
         line["variants"]["gptq_int4_g128"] = gptq
     if e2e:

@@ -289,6 +289,19 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
       B200Q_LAUNCH_OK();
       fixup_ctl = ws.ctl;
     }
+  } else if (strategy == B200Q_TENSOR && !mse && layout == B200Q_KN_BYTES && (K * N) % 4 == 0 &&
+             ((uintptr_t)W % 16 == 0) && ((uintptr_t)out_codes % 4 == 0)) {
+    // streamlined per-tensor route: min/max partials, fold + parameters, vectorised codes
+    const int gsz = minmax_grid(K * N);
+    minmax_partials_kernel<<<gsz, kMinMaxThreads, 0, st>>>(W, K * N, ws.partials);
+    B200Q_LAUNCH_OK();
+    fold_qparams_tensor_kernel<<<1, 256, 0, st>>>(ws.partials, gsz, clip, qs, ws.enc_min, ws.enc_max,
+                                                  out_scale, zp_rows);
+    B200Q_LAUNCH_OK();
+    quantize_flat_kernel<<<kNumSMs * 8, 256, 0, st>>>(W, K * N / 4, qs, out_scale, zp_rows,
+                                                      (unsigned int*)out_codes);
+    B200Q_LAUNCH_OK();
+    return B200Q_OK;
   } else {
     rc = launch_rowstats(W, m, s.rows, ws, st);
     if (rc != B200Q_OK) return rc;

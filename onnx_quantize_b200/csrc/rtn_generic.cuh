@@ -90,6 +90,77 @@ static __global__ void __launch_bounds__(256) quantize_rows_kernel(
   }
 }
 
+// ---- TENSOR strategy, streamlined: fold of the min/max partials + A2 tail + A3 in one single-CTA
+// launch, then a vectorised A4 over the flat array ------------------------------------------------
+static __global__ void __launch_bounds__(256) fold_qparams_tensor_kernel(
+    const float2* __restrict__ partials, int nblocks, float clip, QSpec qs,
+    unsigned int* __restrict__ enc_min, unsigned int* __restrict__ enc_max,
+    float* __restrict__ out_scale, unsigned char* __restrict__ out_zp) {
+  __shared__ float s_mn[8], s_mx[8];
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+    float2 p = partials[i];
+    mn = fminf(mn, p.x); mx = fmaxf(mx, p.y);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    *enc_min = float_to_ordered(mn);
+    *enc_max = float_to_ordered(mx);
+    QParam p = qparam_from_range(fminf(__fmul_rn(mn, clip), 0.0f), fmaxf(__fmul_rn(mx, clip), 0.0f), qs);
+    *out_scale = p.scale;
+    *out_zp = encode_code(p.zp, qs);
+  }
+}
+
+// One (scale, zp) for the whole array; 16 elements per thread and iteration, walked from the END
+// of the array so that the tail of the preceding min/max pass is still in L2.  Codes come from the
+// reciprocal product + magic-number rounding, validated by the exact residual and redone with the
+// IEEE division when a rounding tie cannot be excluded (see rtn_stream.cuh).
+static __global__ void __launch_bounds__(256) quantize_flat_kernel(
+    const float* __restrict__ W, int64_t n4, QSpec qs, const float* __restrict__ scale,
+    const unsigned char* __restrict__ zp, unsigned int* __restrict__ out) {
+  const float s = *scale;
+  const int z = decode_code(*zp, qs);
+  constexpr float kMagic = 12582912.0f;
+  const float delta = qs.bits == 4 ? 1.9073486328125e-06f : 3.0517578125e-05f;   // 2^-19 / 2^-15
+  const float thr = s * (0.5f - delta);
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(s));
+  const float C = kMagic + (float)z, u_lo = kMagic + (float)qs.qmin, u_hi = kMagic + (float)qs.qmax;
+  const float2 inv2 = make_float2(inv, inv), c2 = make_float2(C, C), nc2 = make_float2(-C, -C),
+               ns2 = make_float2(-s, -s);
+  const unsigned int mask = qs.bits == 4 ? 0x0F0F0F0Fu : 0xFFFFFFFFu;
+  const float4* w4 = reinterpret_cast<const float4*>(W);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += stride) {
+    const int64_t i = n4 - 1 - j;
+    const float4 x = __ldg(w4 + i);
+    const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
+    const float2 u01 = __fadd2_rn(__fmul2_rn(x01, inv2), c2), u23 = __fadd2_rn(__fmul2_rn(x23, inv2), c2);
+    const float2 e01 = __ffma2_rn(__fadd2_rn(u01, nc2), ns2, x01);
+    const float2 e23 = __ffma2_rn(__fadd2_rn(u23, nc2), ns2, x23);
+    const float res = fmaxf(fmaxf(fabsf(e01.x), fabsf(e01.y)), fmaxf(fabsf(e23.x), fabsf(e23.y)));
+    unsigned int b0 = __float_as_uint(fminf(fmaxf(u01.x, u_lo), u_hi));
+    unsigned int b1 = __float_as_uint(fminf(fmaxf(u01.y, u_lo), u_hi));
+    unsigned int b2 = __float_as_uint(fminf(fmaxf(u23.x, u_lo), u_hi));
+    unsigned int b3 = __float_as_uint(fminf(fmaxf(u23.y, u_lo), u_hi));
+    if (!(res < thr)) {
+      b0 = (unsigned int)quant_code(x.x, s, z, qs.qmin, qs.qmax);
+      b1 = (unsigned int)quant_code(x.y, s, z, qs.qmin, qs.qmax);
+      b2 = (unsigned int)quant_code(x.z, s, z, qs.qmin, qs.qmax);
+      b3 = (unsigned int)quant_code(x.w, s, z, qs.qmin, qs.qmax);
+    }
+    out[i] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410) & mask;
+  }
+}
+
 // ---- P1: flat nibble packing (core/_pack.py:8-22) -------------------------------------------------
 static __global__ void pack4_flat_kernel(const unsigned char* __restrict__ codes, int64_t n_elements,
                                   unsigned char* __restrict__ out, const MseControl* ctl) {

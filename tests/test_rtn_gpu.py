@@ -156,3 +156,27 @@ def test_stream_kernel_matmul_nbits_bit_exact(cuda, gs, sym, rr, clip):
         assert np.array_equal(b.cpu().numpy(), ob), (k, n)
         assert np.array_equal(bits(s.cpu().numpy()), bits(os_)), (k, n)
         assert z.shape == oz.shape and np.array_equal(z.cpu().numpy(), oz), (k, n)
+
+
+@pytest.mark.parametrize("qt,sym", [("int8", True), ("uint8", False), ("int4", True), ("uint4", False)])
+def test_tensor_route_rounding_ties(cuda, qt, sym):
+    """Per-tensor route (fold + vectorised codes): inputs whose quotient x/s is exactly m + 0.5 must
+    round half to even like np.round — the reciprocal-multiply fast path has to hand them to the
+    exact division."""
+    rng = np.random.default_rng(9)
+    lo, hi = O.qrange(qt, sym, False)
+    step = np.float32(2.0 ** -7)
+    levels = (hi - lo) if not sym else min(hi, -lo)
+    k, n = 256, 512
+    m = rng.integers(0 if not sym else -levels, levels, (k, n)).astype(np.float32)
+    w = ((m + 0.5) * step).astype(np.float32)
+    w[0, 0] = levels * step                       # pins the scale to exactly `step`
+    if not sym:
+        w[0, 1] = 0.0
+    else:
+        w[0, 1] = -levels * step
+    q, s, z = _product(w, qt, "tensor", -1, sym, False, 1.0, False)
+    qo, so, zo = O.rtn_quantize(w, qt, "tensor", -1, sym, False, 1.0, False)
+    assert float(so) == float(step)
+    assert np.array_equal(bits(s), bits(so)) and np.array_equal(as_i8(z, qt), as_i8(zo, qt))
+    assert np.array_equal(as_i8(q, qt), as_i8(qo, qt))
