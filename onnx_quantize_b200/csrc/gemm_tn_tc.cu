@@ -33,6 +33,8 @@ constexpr int kStages1 = 4;
 constexpr int kStages3 = 2;
 constexpr int kThreads1 = 256;
 constexpr int kThreads3 = 384;
+constexpr int kEpiPitch = 36;                            // floats per staged row (144 B, 16-byte aligned)
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;        // 18 KB: one 32 x 32 tile per epilogue warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -164,6 +166,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+  float* epi_stage = (float*)(smem + kStages * kStageBytes + 256);   // 4 warps x 32 x kEpiPitch floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles * p.splits;
@@ -266,47 +269,68 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (!decode_unit(p, unit, mb, nb, t0, t1)) continue;
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t m = (int64_t)mb * kTileM + q * 32 + lane;
+      // TMEM hands every lane one ROW of the chunk; a warp-wide access along rows would touch 32
+      // different 128-byte lines per instruction.  The chunk is transposed through a per-warp
+      // shared-memory tile (pitch 36 floats: conflict-free 128-bit stores and loads) so that each
+      // global access covers 4 rows x 128 contiguous bytes.
+      float* stg = epi_stage + q * (32 * kEpiPitch);
+      const int sub_row = lane >> 3, cg = lane & 7;
 #pragma unroll 1
       for (int c0 = 0; c0 < kTileN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + c0), r);
         const int64_t n0 = (int64_t)nb * kTileN + c0;
-        const bool active = m < p.M && n0 < p.N && !(p.upper_only && n0 + 31 < m);
-        float* dst = p.D + m * p.ldd + n0;
-        const bool full = n0 + 32 <= p.N && (!p.upper_only || n0 >= m) && p.vec_ok;
-        if (!active) {
-          // nothing to write for this lane
-        } else if (full) {
+        const int64_t m_base = (int64_t)mb * kTileM + q * 32;
+        const bool chunk_active = m_base < p.M && n0 < p.N && !(p.upper_only && n0 + 31 < m_base);
+        if (chunk_active) {   // warp-uniform
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 v;
-            v.x = p.alpha * __uint_as_float(r[c]);     v.y = p.alpha * __uint_as_float(r[c + 1]);
-            v.z = p.alpha * __uint_as_float(r[c + 2]); v.w = p.alpha * __uint_as_float(r[c + 3]);
-            if (p.atomic) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x), "f"(v.y),
-                           "f"(v.z), "f"(v.w)
-                           : "memory");
-            } else {
-              if (p.accumulate) {
-                const float4 o = *reinterpret_cast<const float4*>(dst + c);
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-              }
-              *reinterpret_cast<float4*>(dst + c) = v;
-            }
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(stg + lane * kEpiPitch + c) =
+                make_float4(p.alpha * __uint_as_float(r[c]), p.alpha * __uint_as_float(r[c + 1]),
+                            p.alpha * __uint_as_float(r[c + 2]), p.alpha * __uint_as_float(r[c + 3]));
+          __syncwarp();
+          // all loads of the chunk first (they would otherwise serialise behind the stores: the
+          // compiler cannot prove that D rows do not alias)
+          float4 o[8];
+          const bool rmw = !p.atomic && p.accumulate;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t m = m_base + 4 * it + sub_row, n = n0 + 4 * cg;
+            o[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rmw && p.vec_ok && m < p.M && n + 4 <= p.N && (!p.upper_only || n >= m))
+              o[it] = *reinterpret_cast<const float4*>(p.D + m * p.ldd + n);
           }
-        } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int64_t n = n0 + c;
-            if (n < p.N && (!p.upper_only || n >= m)) {
-              const float v = p.alpha * __uint_as_float(r[c]);
-              if (p.atomic) atomicAdd(dst + c, v);
-              else dst[c] = p.accumulate ? dst[c] + v : v;
+          for (int it = 0; it < 8; ++it) {
+            const int row = 4 * it + sub_row;
+            const int64_t m = m_base + row, n = n0 + 4 * cg;
+            float4 v = *reinterpret_cast<const float4*>(stg + row * kEpiPitch + 4 * cg);
+            if (m < p.M && n < p.N && !(p.upper_only && n + 3 < m)) {
+              float* dst = p.D + m * p.ldd + n;
+              const bool full = n + 4 <= p.N && (!p.upper_only || n >= m) && p.vec_ok;
+              if (full) {
+                if (p.atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                               "f"(v.z), "f"(v.w)
+                               : "memory");
+                } else {
+                  v.x += o[it].x; v.y += o[it].y; v.z += o[it].z; v.w += o[it].w;
+                  *reinterpret_cast<float4*>(dst) = v;
+                }
+              } else {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (n + e < p.N && (!p.upper_only || n + e >= m)) {
+                    if (p.atomic) atomicAdd(dst + e, vv[e]);
+                    else dst[e] = p.accumulate ? dst[e] + vv[e] : vv[e];
+                  }
+                }
+              }
             }
           }
         }
-        __syncwarp();   // the next tcgen05.ld is warp-collective
+        __syncwarp();   // the staging tile is reused; the next tcgen05.ld is warp-collective
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tmem_empty[acc]);
@@ -428,11 +452,11 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   const int n_units = p.n_tiles * p.splits;
   const int grid = n_units < kNumSMs ? n_units : kNumSMs;
   if (x3) {
-    const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024 + 256;
+    const size_t smem = (size_t)kStages3 * kStageBytes3 + 1024 + 256 + kEpiBytes;
     B200Q_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tn_tc_kernel<true><<<grid, kThreads3, smem, st>>>(ma, mbm, p);
   } else {
-    const size_t smem = (size_t)kStages1 * kStageBytes1 + 1024 + 256;
+    const size_t smem = (size_t)kStages1 * kStageBytes1 + 1024 + 256 + kEpiBytes;
     B200Q_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tn_tc_kernel<false><<<grid, kThreads1, smem, st>>>(ma, mbm, p);
   }

@@ -9,7 +9,7 @@
 // reference's route and no squaring of the condition number.
 //
 // Blocked, 128 columns at a time; every large product is a gemm_tn (dense.cuh):
-//   potrf : diag block -> C_jj and C_jj^-1 (one CTA, shared memory);  row panel P <- C_jj^-T P;
+//   potrf : diag block -> C_jj and C_jj^-1 (one CTA, the block in registers);  row panel P <- C_jj^-T P;
 //           trailing (upper) <- trailing - P^T P
 //   trtri : V^T = C^-T (lower) row block by row block:
 //           V^T[j, j] = (C_jj^-1)^T;  tmp = C[0:j, j]^T V^T[0:j, 0:j];  V^T[j, 0:j] = -(C_jj^-1)^T tmp
@@ -81,64 +81,115 @@ __global__ void gather_reverse_kernel(const float* __restrict__ H, int64_t K,
 }
 
 // ---- diagonal block: C_jj (upper Cholesky factor, in place) and its inverse ---------------------
-__global__ void __launch_bounds__(256) chol_diag_kernel(float* __restrict__ A, int64_t ld, int64_t j0,
-                                                        int nb, float* __restrict__ DI,
-                                                        int32_t* __restrict__ status) {
-  extern __shared__ float sm[];
-  float* S = sm;                       // [kNB][kPitch] the block, becomes C_jj
-  float* V = sm + kNB * kPitch;        // [kNB][kPitch] its inverse
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < kNB * kNB; idx += 256) {
-    const int r = idx / kNB, c = idx % kNB;
-    float v = (r == c) ? 1.0f : 0.0f;   // identity padding for a short last block
-    if (r < nb && c < nb && c >= r) v = A[(j0 + r) * ld + j0 + c];
-    S[r * kPitch + c] = v;
-    V[r * kPitch + c] = 0.0f;
-  }
-  const int col = tid & (kNB - 1), half = tid >> 7;   // two threads per column, rows interleaved
-  for (int k = 0; k < nb; ++k) {
-    __syncthreads();
-    float piv = S[k * kPitch + k];
-    if (!(piv > 0.0f)) {                // also catches NaN: LAPACK spotrf's `ajj <= 0 || isnan`
-      if (tid == 0) atomicExch(status, 1);
-      piv = 1.0f;
+// One CTA of 16 x 16 threads holds the 128 x 128 block in REGISTERS: thread (ty, tx) owns the 8 x 8
+// elements (r = ty + 16 i, c = tx + 16 j), so the rank-1 update of step k is 64 predicated FMAs per
+// thread on values broadcast through a 128-float row (and column) buffer — two barriers per step,
+// no shared-memory traffic for the matrix itself.  The inverse V = C^-1 uses the same outer-product
+// form run backwards: T = I; for k = n-1 .. 0: V[k,:] = T[k,:] / C[k,k]; T[r,:] -= C[r,k] V[k,:] (r < k).
+__global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A, int64_t ld, int64_t j0,
+                                                           int nb, float* __restrict__ DI,
+                                                           int32_t* __restrict__ status) {
+  __shared__ float rowbuf[kNB], colbuf[kNB];
+  __shared__ float s_piv;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float e[8][8], t[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      float v = (r == c) ? 1.0f : 0.0f;   // identity padding for a short last block
+      if (r < nb && c < nb && c >= r) v = A[(j0 + r) * ld + j0 + c];
+      e[i][j] = v;
+      t[i][j] = (r == c) ? 1.0f : 0.0f;
     }
-    const float d = sqrtf(piv), inv = 1.0f / d;
-    __syncthreads();
-    if (half == 0) {
-      if (col == k) S[k * kPitch + k] = d;
-      else if (col > k) S[k * kPitch + col] *= inv;
-    }
-    __syncthreads();
-    if (col > k) {
-      const float ckc = S[k * kPitch + col];
-      for (int r = k + 1 + half; r <= col; r += 2)
-        S[r * kPitch + col] = fmaf(-S[k * kPitch + r], ckc, S[r * kPitch + col]);
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < nb * nb; idx += 256) {
-    const int r = idx / nb, c = idx % nb;
-    if (c >= r) A[(j0 + r) * ld + j0 + c] = S[r * kPitch + c];
-  }
-  // V = S^-1 (upper): column c by back substitution, rows aligned across threads so that S[r][k]
-  // is a broadcast and V[k][c] is conflict-free
-  if (half == 0) V[col * kPitch + col] = 1.0f / S[col * kPitch + col];
-  __syncthreads();
-  if (half == 0) {
-    for (int r = kNB - 2; r >= 0; --r) {
-      if (col > r) {
-        float acc = 0.0f;
-        for (int k = r + 1; k <= col; ++k) acc = fmaf(S[r * kPitch + k], V[k * kPitch + col], acc);
-        V[r * kPitch + col] = -acc / S[r * kPitch + r];
+  // ---- factorization ----
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll 1
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k = 16 * kb + kk;
+      if (k >= nb) break;
+      if (ty == kk && tx == kk) s_piv = e[kb][kb];
+      __syncthreads();
+      float piv = s_piv;
+      if (!(piv > 0.0f)) {                // also catches NaN: LAPACK spotrf's `ajj <= 0 || isnan`
+        if (tid == 0) atomicExch(status, 1);
+        piv = 1.0f;
       }
+      const float d = sqrtf(piv), inv = 1.0f / d;
+      if (ty == kk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = tx + 16 * j;
+          if (c > k) e[kb][j] *= inv;
+          else if (c == k) e[kb][j] = d;
+          rowbuf[c] = e[kb][j];
+        }
+      }
+      __syncthreads();
+      float rv[8], cv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rv[i] = rowbuf[ty + 16 * i]; cv[i] = rowbuf[tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = ty + 16 * i, c = tx + 16 * j;
+          if (r > k && c >= r) e[i][j] = fmaf(-rv[i], cv[j], e[i][j]);
+        }
     }
   }
-  __syncthreads();
-  for (int idx = tid; idx < kNB * kNB; idx += 256) {
-    const int r = idx / kNB, c = idx % kNB;
-    DI[idx] = V[r * kPitch + c];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      if (r < nb && c < nb && c >= r) A[(j0 + r) * ld + j0 + c] = e[i][j];
+    }
+  // ---- inverse of the upper factor ----
+#pragma unroll
+  for (int kb = 7; kb >= 0; --kb) {
+#pragma unroll 1
+    for (int kk = 15; kk >= 0; --kk) {
+      const int k = 16 * kb + kk;
+      if (k >= nb) continue;              // padded part: identity
+      __syncthreads();                    // previous step's buffers are free
+      if (ty == kk && tx == kk) s_piv = e[kb][kb];
+      if (tx == kk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) colbuf[ty + 16 * i] = e[i][kb];   // C[r][k]
+      }
+      __syncthreads();
+      const float inv = 1.0f / s_piv;
+      if (ty == kk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = tx + 16 * j;
+          if (c >= k) t[kb][j] *= inv;    // V[k][c]
+          rowbuf[c] = (c >= k) ? t[kb][j] : 0.0f;
+        }
+      }
+      __syncthreads();
+      float sv[8], vv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sv[i] = colbuf[ty + 16 * i]; vv[i] = rowbuf[tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = ty + 16 * i, c = tx + 16 * j;
+          if (r < k && c >= k) t[i][j] = fmaf(-sv[i], vv[j], t[i][j]);
+        }
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      DI[r * kNB + c] = (c >= r) ? t[i][j] : 0.0f;
+    }
 }
 
 // VT[j0+r][j0+c] = DI[c][r] (the transposed inverse of a diagonal block, lower triangular)
@@ -230,15 +281,12 @@ int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int ac
   }
   B200Q_CUDA_OK(cudaMemsetAsync(ws.VT, 0, (size_t)K * K * 4, st));
 
-  const size_t diag_smem = (size_t)2 * kNB * kPitch * sizeof(float);
-  B200Q_CUDA_OK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)diag_smem));
   GemmTN g;
   // ---- potrf (upper, right-looking) ----
   for (int64_t j0 = 0, jb = 0; j0 < K; j0 += kNB, ++jb) {
     const int nb = (int)(K - j0 < kNB ? K - j0 : kNB);
     float* DIj = ws.DI + jb * kNB * kNB;
-    chol_diag_kernel<<<1, 256, diag_smem, st>>>(ws.Hr, K, j0, nb, DIj, status);
+    chol_diag_kernel<<<1, 256, 0, st>>>(ws.Hr, K, j0, nb, DIj, status);
     B200Q_LAUNCH_OK();
     const int64_t rest = K - j0 - nb;
     if (rest <= 0) break;
