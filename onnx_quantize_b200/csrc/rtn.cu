@@ -165,6 +165,11 @@ __global__ void pow_approx_kernel(const float* __restrict__ x, int64_t n, float*
     out[i] = pow_norm_approx(fabsf(x[i]));
 }
 
+template <int GS>
+static void launch_stream_batch(const StreamBatch& b, cudaStream_t st) {
+  rtn_group_nbits4_batch_kernel<GS><<<(unsigned)b.total_tiles, kStreamThreads, 0, st>>>(b);
+}
+
 int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, int64_t group_size,
                  int symmetric, int reduce_range, double clip_ratio, int mse, float* out_scale,
                  unsigned char* out_zp, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -363,6 +368,48 @@ int b200q_rtn_quantize_batch(const b200q_rtn_job* jobs, int64_t n_jobs, int qtyp
                              double clip_ratio, int mse, int layout, void* workspace,
                              size_t workspace_bytes, b200q_stream_t stream) {
   B200Q_REQUIRE(jobs && n_jobs >= 0, B200Q_ERR_INVALID_ARG, "bad job list");
+  // The HBM-bound configuration (no search, uint4, MatMulNBits layout, fused group sizes) goes out
+  // as one launch per <= 256 jobs; everything else is a loop of single-weight calls.
+  QSpec bqs;
+  const bool stream_cfg = !mse && layout == B200Q_MATMUL_NBITS && strategy == B200Q_GROUP &&
+                          make_qspec(qtype, symmetric, reduce_range, &bqs) && bqs.bits == 4 &&
+                          !bqs.is_signed && (group_size == 16 || group_size == 32 || group_size == 64 ||
+                                             group_size == 128) &&
+                          clip_ratio > 0.0 && clip_ratio <= 1.0;
+  bool all_ok = stream_cfg && n_jobs > 0;
+  for (int64_t i = 0; all_ok && i < n_jobs; ++i) {
+    const b200q_rtn_job& j = jobs[i];
+    all_ok = j.W && j.out_codes && j.out_scale && j.out_zp && j.K > 0 && j.N > 0 && j.K % group_size == 0 &&
+             j.N % 16 == 0 && j.K < (1ll << 31) && j.N < (1ll << 31) && ((uintptr_t)j.W % 16 == 0) &&
+             ((uintptr_t)j.out_codes % 16 == 0);
+  }
+  if (all_ok) {
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t first = 0; first < n_jobs;) {
+      StreamBatch b;
+      b.qs = bqs; b.clip = (float)clip_ratio; b.n_jobs = 0; b.total_tiles = 0;
+      while (first < n_jobs && b.n_jobs < kStreamMaxJobs) {
+        const b200q_rtn_job& j = jobs[first];
+        const int64_t nbx = ceil_div(j.N, kStreamCols), nby = ceil_div(j.K / group_size, 2);
+        if ((int64_t)b.total_tiles + nbx * nby > 0x7fffffffll) break;
+        StreamJob& sj = b.jobs[b.n_jobs++];
+        sj.W = j.W; sj.out_codes = (unsigned char*)j.out_codes; sj.out_scale = j.out_scale;
+        sj.zp_packed = (unsigned char*)j.out_zp; sj.K = (int)j.K; sj.N = (int)j.N;
+        sj.tile_begin = b.total_tiles; sj.nbx = (int)nbx;
+        b.total_tiles += (int)(nbx * nby);
+        ++first;
+      }
+      B200Q_REQUIRE(b.n_jobs > 0, B200Q_ERR_UNSUPPORTED, "a single weight exceeds 2^31 tiles");
+      switch (group_size) {
+        case 16: launch_stream_batch<16>(b, st); break;
+        case 32: launch_stream_batch<32>(b, st); break;
+        case 64: launch_stream_batch<64>(b, st); break;
+        default: launch_stream_batch<128>(b, st); break;
+      }
+      B200Q_LAUNCH_OK();
+    }
+    return B200Q_OK;
+  }
   for (int64_t i = 0; i < n_jobs; ++i) {
     const b200q_rtn_job& j = jobs[i];
     int rc = b200q_rtn_quantize(j.W, j.K, j.N, qtype, strategy, group_size, symmetric, reduce_range,

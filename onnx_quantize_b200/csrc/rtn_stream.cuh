@@ -39,9 +39,27 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// One job of a batched launch: a (K,N) weight and its three outputs.
+struct StreamJob {
+  const float* W;
+  unsigned char* out_codes;
+  float* out_scale;
+  unsigned char* zp_packed;
+  int K, N;
+  int tile_begin;   // first linear tile index of this job inside the launch
+  int nbx;          // column tiles (ceil(N / 128))
+};
+constexpr int kStreamMaxJobs = 256;   // 48 B each: 12 KB of kernel parameters
+struct StreamBatch {
+  StreamJob jobs[kStreamMaxJobs];
+  int n_jobs;
+  int total_tiles;
+  QSpec qs;
+  float clip;
+};
+
 template <int GS>
-__global__ void __launch_bounds__(kStreamThreads, 2)
-rtn_group_nbits4_kernel(const __grid_constant__ FusedArgs a) {
+__device__ __forceinline__ void stream_tile(const FusedArgs& a, int bx, int by) {
   static_assert(GS % 16 == 0 && GS <= 128, "group sizes 16..128");
   constexpr int R = GS / 8;                 // consecutive rows per warp (and thread)
   constexpr int HR = R < 8 ? R : 8;         // rows per validated chunk
@@ -55,21 +73,21 @@ rtn_group_nbits4_kernel(const __grid_constant__ FusedArgs a) {
   __shared__ __align__(16) unsigned int stage[16][kStreamCols];   // [word of the column block][column]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t n0 = (int64_t)blockIdx.x * kStreamCols;
+  const int64_t n0 = (int64_t)bx * kStreamCols;
   const int64_t n = n0 + 4 * lane;
   const bool col_ok = n < a.N;              // N % 4 == 0 on this path
   const QSpec qs = a.qs;
   constexpr float kMagic = 12582912.0f;                       // 1.5 * 2^23: ulp 1, integer in the low bits
   constexpr float kDelta = 1.9073486328125e-06f;              // 2^-19 > 2^-24 * (|code range| + 2)
   const float u_lo = kMagic + (float)qs.qmin, u_hi = kMagic + (float)qs.qmax;
-  // A CTA walks the two groups (2*blockIdx.y, +1) whose zero points share one byte of the
+  // A CTA walks the two groups (2*by, +1) whose zero points share one byte of the
   // MatMulNBits zero-point tensor (qrules/_common.py:96-121: low nibble = even g, an odd count is
   // padded with 0x8; not packed when there is a single group).
   unsigned int zp_even = 0;
 
 #pragma unroll 1
   for (int gi = 0; gi < 2; ++gi) {
-    const int64_t g = 2 * (int64_t)blockIdx.y + gi;
+    const int64_t g = 2 * (int64_t)by + gi;
     if (g >= a.G) break;
 
     float4 v[R];
@@ -233,6 +251,35 @@ rtn_group_nbits4_kernel(const __grid_constant__ FusedArgs a) {
     }
     __syncthreads();   // staging and reduction buffers are reused by the second group
   }
+}
+
+template <int GS>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+rtn_group_nbits4_kernel(const __grid_constant__ FusedArgs a) {
+  stream_tile<GS>(a, blockIdx.x, blockIdx.y);
+}
+
+// A whole model's weights in one launch: linear tile index -> (job, column tile, group pair) by
+// binary search over the jobs' first-tile table (kernel parameters, i.e. constant memory).  Small
+// matrices no longer pay their own launch tail: the 224 matrices of a Llama-3-8B-shaped set become
+// one grid of ~100k tiles.
+template <int GS>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+rtn_group_nbits4_batch_kernel(const __grid_constant__ StreamBatch b) {
+  const int tile = blockIdx.x;
+  int lo = 0, hi = b.n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (b.jobs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+  }
+  const StreamJob& j = b.jobs[lo];
+  FusedArgs a;
+  a.W = j.W; a.K = j.K; a.N = j.N; a.G = j.K / GS; a.qs = b.qs; a.clip = b.clip;
+  a.layout = B200Q_MATMUL_NBITS;
+  a.out_codes = j.out_codes; a.out_scale = j.out_scale; a.zp_rows = nullptr; a.zp_packed = j.zp_packed;
+  a.masks = nullptr; a.enc_min = nullptr; a.enc_max = nullptr; a.ctl = nullptr; a.run_if_state = 0;
+  const int t = tile - j.tile_begin;
+  stream_tile<GS>(a, t % j.nbx, t / j.nbx);
 }
 
 }  // namespace b200q

@@ -180,3 +180,21 @@ def test_tensor_route_rounding_ties(cuda, qt, sym):
     assert float(so) == float(step)
     assert np.array_equal(bits(s), bits(so)) and np.array_equal(as_i8(z, qt), as_i8(zo, qt))
     assert np.array_equal(as_i8(q, qt), as_i8(qo, qt))
+
+
+def test_batched_stream_launch_matches_single_calls(cuda):
+    """b200q_rtn_quantize_batch sends the HBM-bound configuration out as ONE launch for the whole
+    job list (job table in kernel parameters); results must equal per-weight calls and the oracle."""
+    from onnx_quantize_b200 import device_api as D
+    rng = np.random.default_rng(21)
+    shapes = [(256, 128), (128, 48), (384, 1040 + 8), (1024, 256), (128, 16), (640, 4096)]
+    ws = [torch.from_numpy((rng.standard_normal(s) * 0.02).astype(np.float32)).to(cuda) for s in shapes]
+    for gs in (128, 32):
+        outs = D.rtn_quantize_batch(ws, "uint4", "group", gs, False, False, 0.9, False, layout="matmul_nbits")
+        for w, (b, s, z) in zip(ws, outs):
+            b1, s1, z1 = D.rtn_quantize(w, "uint4", "group", gs, False, False, 0.9, False, layout="matmul_nbits")
+            assert torch.equal(b, b1) and torch.equal(s, s1) and torch.equal(z, z1)
+            qo, so, zo = O.rtn_quantize(w.cpu().numpy(), "uint4", "group", gs, False, False, 0.9, False)
+            ob, os_, oz = O.matmul_nbits_layout(qo, so, zo, gs, 4)
+            assert np.array_equal(b.cpu().numpy(), ob) and np.array_equal(z.cpu().numpy(), oz)
+            assert np.array_equal(bits(s.cpu().numpy()), bits(os_))
