@@ -163,23 +163,78 @@ def make_weights(torch, device, layers, rank):
 # tokens, calibration tokens split over the ranks (NCCL sum-reduce of every Hessian to the rank that
 # owns its solve), solves sharded over the ranks.  Strong scaling: the sample is fixed.
 # ------------------------------------------------------------------------------------------------
-GPTQ_GROUPS = [("qkv", 4096, [(4096, 4096), (4096, 1024), (4096, 1024)]), ("o", 4096, [(4096, 4096)]),
-               ("gate_up", 4096, [(4096, 14336), (4096, 14336)]), ("down", 14336, [(14336, 4096)])]
+GPTQ_MODELS = {
+    # name: (layers in the model, [(Hessian name, K, [(K, N) weights sharing that input])])
+    "llama3_8b": (32, [("qkv", 4096, [(4096, 4096), (4096, 1024), (4096, 1024)]), ("o", 4096, [(4096, 4096)]),
+                       ("gate_up", 4096, [(4096, 14336), (4096, 14336)]), ("down", 14336, [(14336, 4096)])]),
+    "gemma3_1b": (26, [("qkv", 1152, [(1152, 1024), (1152, 256), (1152, 256)]), ("o", 1024, [(1024, 1152)]),
+                       ("gate_up", 1152, [(1152, 6912), (1152, 6912)]), ("down", 6912, [(6912, 1152)])]),
+}
 GPTQ_SAMPLES, GPTQ_SEQ = 128, 2048
 
 
-def run_gptq_variant(args, torch, dist, device, world, rank):
+def gptq_cpu_reference(groups, model_layers):
+    """The reference's CPU path for the same work, timed on a bounded sample and extrapolated
+    (SURVEY.md §8d): `_accumulate_hessian` on 2 x 2048 tokens per distinct K (sgemm is linear in
+    tokens), `_gptq` on one small weight per distinct K (the Python row loop is linear in K*N)."""
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(0)
+    tokens = GPTQ_SAMPLES * GPTQ_SEQ
+    hess_s, solve_s, measured = 0.0, 0.0, 0.0
+    # the Python row loop of `_gptq` (gptq.py:164-201): cost per row = a + b * N, measured once
+    k0 = min(g[1] for g in groups)
+    h0 = np.eye(k0, dtype=np.float32)
+    loop = []
+    for n_small in (64, 192):
+        w = (rng.standard_normal((k0, n_small)) * 0.02).astype(np.float32)
+        t0 = time.perf_counter()
+        O.gptq(w, h0, "int4", "group", 128, True, mode="reference")
+        loop.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    O.hinv_cholesky_upper(h0, 0.01)
+    fact0 = time.perf_counter() - t0
+    measured += sum(loop) + fact0
+    per_row_col = max(loop[1] - loop[0], 0.0) / (128 * k0)
+    per_row = max(loop[0] - fact0 - per_row_col * 64 * k0, 0.0) / k0
+    per_k = {}
+    for _, k, shapes in groups:
+        if k not in per_k:
+            x = rng.standard_normal((2, GPTQ_SEQ, k)).astype(np.float32)
+            t0 = time.perf_counter()
+            h, _ = O.accumulate_hessian(x, np.zeros((k, k), np.float32), 0)
+            th = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            O.hinv_cholesky_upper(h + np.eye(k, dtype=np.float32) * np.float32(0.1 * np.trace(h) / k), 0.01)
+            tf = time.perf_counter() - t0          # cholesky + inv + cholesky: once per WEIGHT in the reference
+            per_k[k] = (th * tokens / (2 * GPTQ_SEQ), tf)
+            measured += th + tf
+        th_full, tf = per_k[k]
+        # the reference accumulates one Hessian PER NODE (calibrate.py:296-307), not per shared input
+        hess_s += th_full * len(shapes)
+        solve_s += sum(tf + k * (per_row + per_row_col * n) for _, n in shapes)
+    return {"kind": "port", "cores": os.cpu_count(), "s_per_layer_extrapolated": hess_s + solve_s,
+            "s_per_model_extrapolated": (hess_s + solve_s) * model_layers,
+            "hessian_s_per_layer": hess_s, "solve_s_per_layer": solve_s, "measured_seconds": measured,
+            "sample": "np.matmul Hessian on 2x2048 tokens per distinct K scaled to 128x2048; LAPACK "
+                      "cholesky+inv+cholesky once per distinct K; the Python row loop of _gptq timed on 64 and "
+                      "192 columns at the smallest K and scaled as K*(a + b*N); one Hessian and one "
+                      "factorization per node, as the reference does"}
+
+
+def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", layers=None, cpu_ref=False):
+    model_layers, GPTQ_GROUPS = GPTQ_MODELS[model]
     from onnx_quantize_b200 import gptq_device as G
     from onnx_quantize_b200.core._dtypes import QuantType
     from onnx_quantize_b200.hessian import hessian_accumulate
     from onnx_quantize_b200.parallel.shard import assign_units
 
-    layers = args.gptq_layers
+    layers = layers or args.gptq_layers
     tokens = GPTQ_SAMPLES * GPTQ_SEQ
     t_local = tokens // world
     gen = torch.Generator(device=device)
     gen.manual_seed(4242 + rank)
-    xs = {k: torch.randn((t_local, k), generator=gen, device=device, dtype=torch.float32) for k in (4096, 14336)}
+    xs = {k: torch.randn((t_local, k), generator=gen, device=device, dtype=torch.float32)
+          for k in sorted({g[1] for g in GPTQ_GROUPS})}
     ws = {}
     for _, _, shapes in GPTQ_GROUPS:
         for shp in shapes:
@@ -252,13 +307,13 @@ def run_gptq_variant(args, torch, dist, device, world, rank):
         pass
     bf16 = float(peaks.get("bf16_tflops_sustained", 1393.9))
     tf = mma_flops / world / (hess_ms * 1e-3) / 1e12       # per GPU: every rank contracts tokens/world
-    return {
-        "workload": f"cfg5: GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
-                    f"Llama-3-8B-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
+    out = {
+        "workload": f"GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
+                    f"{model}-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
                     f"{GPTQ_SAMPLES}x{GPTQ_SEQ} calibration tokens split over {world} rank(s)",
         "precision": args.gptq_precision, "scaling": "strong", "n_gpus": world,
-        "s_per_step": total_ms * 1e-3, "s_per_model_extrapolated": total_ms * 1e-3 * 32 / layers,
-        "extrapolation": f"x{32 / layers:g}: the 32 layers are identical in shape",
+        "s_per_step": total_ms * 1e-3, "s_per_model_extrapolated": total_ms * 1e-3 * model_layers / layers,
+        "extrapolation": f"x{model_layers / layers:g}: the {model_layers} layers are identical in shape",
         "hessian_s": hess_ms * 1e-3, "hessian_reduce_s": red_ms * 1e-3, "solve_s": solve_ms * 1e-3,
         "hessian_tflops_algorithmic": flops / (hess_ms * 1e-3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "hessian_kernel", "achieved": tf, "unit": "TFLOP/s",
@@ -268,6 +323,11 @@ def run_gptq_variant(args, torch, dist, device, world, rank):
                                     "tiles only, x3 products in 3xTF32 mode) / Hessian time",
                      "flops": flops},
     }
+    del xs, ws, hs
+    torch.cuda.empty_cache()
+    if cpu_ref and rank == 0:
+        out["cpu_reference"] = gptq_cpu_reference(GPTQ_GROUPS, model_layers)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -434,7 +494,11 @@ def run_gpu_arm(args):
         del plans, weights
         D.dev.release_workspaces()
         torch.cuda.empty_cache()
-        gptq = run_gptq_variant(args, torch, dist, device, world, rank)
+        want_cpu = not args.no_cpu_baseline and world == 1
+        gptq = {"gptq_int4_g128_llama3_8b": run_gptq_variant(args, torch, dist, device, world, rank, "llama3_8b",
+                                                             cpu_ref=want_cpu),
+                "gptq_int4_g128_gemma3_1b": run_gptq_variant(args, torch, dist, device, world, rank, "gemma3_1b",
+                                                             layers=26)}
 
     if rank != 0:
         if world > 1:
@@ -478,7 +542,7 @@ def run_gpu_arm(args):
     if small:
         line["variants"].update(small)
     if gptq:
-        line["variants"]["gptq_int4_g128"] = gptq
+        line["variants"].update(gptq)
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
