@@ -1,15 +1,18 @@
-"""Small fixed workload for ncu: the streaming (no search) and the two-tier MSE group kernels on one
-gate_proj-shaped weight (4096 x 14336) and one q_proj-shaped weight, three launches each."""
-import sys, os
+"""Small fixed workload for ncu: the batched streaming kernel (no search) and the two-tier MSE kernel
+on one gate_proj-shaped (4096 x 14336) and one q_proj-shaped weight, two passes each."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
 from onnx_quantize_b200 import device_api as D
 
 torch.manual_seed(0)
-for shape in ((4096, 14336), (4096, 4096)):
-    w = torch.randn(shape, device="cuda") * 0.02
-    for mse in (False, True):
-        for _ in range(3):
-            D.rtn_quantize(w, "uint4", "group", 128, False, False, 0.9, mse, layout="matmul_nbits")
+ws = [torch.randn(shape, device="cuda") * 0.02 for shape in ((4096, 14336), (4096, 4096))]
+for mse in (False, True):
+    plan = D.RtnBatchPlan(ws, "uint4", "group", 128, False, False, 0.9, mse, layout="matmul_nbits")
+    for _ in range(2):
+        plan.run()
     torch.cuda.synchronize()
 print("ok")
