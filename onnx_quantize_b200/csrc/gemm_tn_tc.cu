@@ -356,7 +356,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          hi[v] = h;
+          // `hi` is not written back: kind::tf32 ignores the 13 low mantissa bits of its 32-bit
+          // operands (truncation), so the raw value already IS the hi term — one third less
+          // shared-memory write traffic for the splitter
           lo[v] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

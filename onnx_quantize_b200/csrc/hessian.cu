@@ -19,6 +19,7 @@
 // into hi = tf32(x) and lo = x - hi so that D += Ah*Bh + Ah*Bl + Al*Bh recovers fp32 accuracy.
 // Two 256-column accumulators (all 512 TMEM columns) double-buffer MMA against the epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -349,7 +350,9 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          hi[v] = h;
+          // `hi` is not written back: kind::tf32 ignores the 13 low mantissa bits of its 32-bit
+          // operands (truncation), so the raw value already IS the hi term — one third less
+          // shared-memory write traffic for the splitter
           lo[v] = l;
         }
         // generic-proxy writes must be visible to the tensor core's async proxy reads
@@ -501,6 +504,10 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
   // Short inputs are split further so that every SM has work.
   const int64_t stages_total = ceil_div(T, kTT);
   int64_t chunk_stages = precision == B200Q_TF32X3 ? 512 / kTT : 4096 / kTT;
+  if (const char* e = getenv("B200Q_HESSIAN_CHUNK")) {   // experiment knob (tokens per unit)
+    const long v = atol(e);
+    if (v >= kTT) chunk_stages = v / kTT;
+  }
   while (chunk_stages > 4 && p.n_tiles * ceil_div(stages_total, chunk_stages) < 2 * kNumSMs) chunk_stages /= 2;
   p.t_per_split = chunk_stages * kTT;
   p.splits = (int)ceil_div(T, p.t_per_split);
