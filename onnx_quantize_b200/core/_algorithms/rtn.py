@@ -49,8 +49,8 @@ def _shape_like_reference(scale: np.ndarray, zp: np.ndarray, strategy: Quantizat
     """tensor → 0-d, channel → (N,), group → (N*G, 1) (reference rtn.py:101-104)."""
     if strategy == QuantizationStrategy.TENSOR:
         return scale.reshape(()), zp.reshape(())
-    if strategy == QuantizationStrategy.CHANNEL:
-        return scale.reshape(-1), zp.reshape(-1)
+    if strategy == QuantizationStrategy.CHANNEL:   # np.squeeze of (N,1): a single channel becomes 0-d
+        return np.squeeze(scale.reshape(-1, 1)), np.squeeze(zp.reshape(-1, 1))
     return scale.reshape(-1, 1), zp.reshape(-1, 1)
 
 

@@ -198,3 +198,42 @@ def test_batched_stream_launch_matches_single_calls(cuda):
             ob, os_, oz = O.matmul_nbits_layout(qo, so, zo, gs, 4)
             assert np.array_equal(b.cpu().numpy(), ob) and np.array_equal(z.cpu().numpy(), oz)
             assert np.array_equal(bits(s.cpu().numpy()), bits(os_))
+
+
+@pytest.mark.parametrize("mse", [0, 1])
+@pytest.mark.parametrize("k,n,gs", [(128, 48, 128), (384, 80, 128), (96, 4112, 32), (64, 16, 16), (640, 208, 64)])
+def test_no_out_of_bounds_writes_through_the_c_abi(cuda, k, n, gs, mse):
+    """Guard bands around every output buffer of b200q_rtn_quantize (MatMulNBits layout, ragged
+    tiles): compute-sanitizer is not available on the GPU pool, so the outputs are carved out of
+    one canary-filled allocation and the bands are checked after the call."""
+    from onnx_quantize_b200 import _lib, _device
+    lib = _lib.load()
+    rng = np.random.default_rng(k + n)
+    w = torch.from_numpy((rng.standard_normal((k, n)) * 0.02).astype(np.float32)).to(cuda)
+    g = k // gs
+    sizes = [n * k // 2, 4 * n * g, n * ((g + 1) // 2 if g > 1 else g)]      # codes, scales, packed zp
+    band = 256
+    offs, total = [], band
+    for sz in sizes:
+        offs.append(total)
+        total += (sz + 255) // 256 * 256 + band
+    buf = torch.full((total,), 0xAB, dtype=torch.uint8, device=cuda)
+    ws = torch.empty(lib.b200q_rtn_workspace_bytes(k, n, 2, gs, mse) + 512, dtype=torch.uint8, device=cuda)
+    ws.fill_(0xCD)
+    base = buf.data_ptr()
+    rc = lib.b200q_rtn_quantize(w.data_ptr(), k, n, _lib.QTYPE["uint4"], 2, gs, 0, 0, 0.9, mse,
+                                _lib.LAYOUT["matmul_nbits"], base + offs[0], base + offs[1], base + offs[2],
+                                None, ws.data_ptr(), ws.numel() - 512, _device.stream_ptr())
+    assert rc == 0, lib.b200q_last_error()
+    torch.cuda.synchronize()
+    host = buf.cpu().numpy()
+    used = np.zeros(total, bool)
+    for o, sz in zip(offs, sizes):
+        used[o:o + sz] = True
+    assert np.all(host[~used] == 0xAB), "write outside an output buffer"
+    assert np.all(ws[-512:].cpu().numpy() == 0xCD), "write past the declared workspace size"
+    qo, so, zo = O.rtn_quantize(w.cpu().numpy(), "uint4", "group", gs, False, False, 0.9, bool(mse))
+    ob, os_, oz = O.matmul_nbits_layout(qo, so, zo, gs, 4)
+    assert np.array_equal(host[offs[0]:offs[0] + sizes[0]], ob.reshape(-1))
+    assert np.array_equal(host[offs[1]:offs[1] + sizes[1]].view(np.float32).view(np.uint32), bits(os_).reshape(-1))
+    assert np.array_equal(host[offs[2]:offs[2] + sizes[2]], oz.reshape(-1))
