@@ -365,22 +365,23 @@ def run_small_variants(torch, device, peak):
     out["cfg1_int8_sym_tensor"] = {
         "workload": "cfg1: RTN int8 symmetric per-tensor, 2 x (4096x4096) f32 (codes one byte per element)",
         "ms_per_step": ms, "value": 4 * elts / (ms * 1e-3) / 1e9, "unit": "GB/s",
-        "roofline": {"bound": "hbm", "kernel": "minmax_partials_kernel + quantize_rows_kernel",
+        "roofline": {"bound": "hbm", "kernel": "minmax_partials_kernel + quantize_flat_kernel",
                      "achieved": 5.0 * elts / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 5.0 * elts / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_element": 5.0,
                      "note": "two passes over W (global min/max must precede any code); the second pass "
                              "re-reads the 64 MiB weight from L2"}}
     # cfg3: static-calibration min/max of 100 x 512 x 4096 activations in 10 batches, then A3
     acts = [torch.randn((10, 512, 4096), generator=gen, device=device) for _ in range(10)]
-    pairs = torch.empty((10, 2), dtype=torch.float32, device=device)
+    slots = torch.empty((10, D.minmax_partials_stride(), 2), dtype=torch.float32, device=device)
+    counts = torch.zeros((10,), dtype=torch.int32, device=device)
     state = torch.zeros((2,), dtype=torch.float32, device=device)
     valid = torch.zeros((1,), dtype=torch.int32, device=device)
 
-    def cfg3():
+    def cfg3():   # what MinMaxCalibrator.collect x 10 + compute_range launch: 10 reductions, 1 fold+merge, A3
         valid.zero_()
         for i, x in enumerate(acts):
-            D.minmax_reduce(x.reshape(-1), pairs[i])
-        D.minmax_merge(state, valid, pairs, 0.0)
+            D.minmax_partials(x.reshape(-1), slots[i], counts[i:i + 1])
+        D.minmax_fold_merge(state, valid, slots, counts, 10, 0.0)
         D.qparams(state[0:1].clamp(max=0), state[1:2].clamp(min=0), QuantType.QUInt8)
 
     ms = time_ms(cfg3, iters=5)

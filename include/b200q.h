@@ -188,6 +188,19 @@ int b200q_pack_matmul_nbits(const void* codes, int64_t K, int64_t N, int64_t gro
 size_t b200q_minmax_workspace_bytes(int64_t n);
 int b200q_minmax_reduce(const float* x, int64_t n, float* minmax_batch, void* workspace,
                         size_t workspace_bytes, b200q_stream_t stream);
+/* One launch per batch, one for all folds: b200q_minmax_partials only writes the per-CTA partial
+ * (min, max) pairs of one batch (into a slot of b200q_minmax_partials_stride() float2 entries, and
+ * the number of valid entries into the DEVICE int *count), and b200q_minmax_fold_merge later folds
+ * any number of such slots (slot b at partials + b*stride, counts[b] entries, both on the device)
+ * and applies the running update in batch order — i.e.
+ * b200q_minmax_reduce x n + b200q_minmax_merge in n + 1 launches instead of 2n + 1.  out_pairs
+ * (optional, f32[2*n_batches]) receives the per-batch pairs. */
+size_t b200q_minmax_partials_stride(void);
+int b200q_minmax_partials(const float* x, int64_t n, void* partials, int32_t* count,
+                          b200q_stream_t stream);
+int b200q_minmax_fold_merge(float* state, int32_t* state_valid, const void* partials,
+                            const int32_t* counts, int64_t n_batches, double momentum,
+                            float* out_pairs, b200q_stream_t stream);
 /* state f32[2] (valid iff *state_valid != 0) <- fold `n_batches` (min,max) pairs in order:
  * momentum == 0: running min / max (minmax.py:63-64); else EMA m*old + (1-m)*cur (minmax.py:55-60) */
 int b200q_minmax_merge(float* state, int32_t* state_valid, const float* batch_pairs,

@@ -68,6 +68,9 @@ _SIGNATURES = {
     "b200q_minmax_workspace_bytes": (_sz, [_i64]),
     "b200q_minmax_reduce": (_i32, [_ptr, _i64, _ptr, _ptr, _sz, _ptr]),
     "b200q_minmax_merge": (_i32, [_ptr, _ptr, _ptr, _i64, _f64, _ptr]),
+    "b200q_minmax_partials_stride": (_sz, []),
+    "b200q_minmax_partials": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr]),
+    "b200q_minmax_fold_merge": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _f64, _ptr, _ptr]),
 }
 _OPTIONAL_SIGNATURES = {
     "b200q_hessian_workspace_bytes": (_sz, [_i64, _i64, _i32]),

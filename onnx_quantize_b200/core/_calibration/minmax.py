@@ -1,10 +1,10 @@
 """MinMax activation calibrator on the GPU — mirrors the reference's
 ``core/_calibration/minmax.py`` (``MinMaxCalibrator`` :11-87).
 
-``collect`` launches one streaming min/max reduction per batch and appends the resulting
-(min, max) pair to a device-side list; nothing is synchronised or copied back until
-``compute_range`` (or ``.data``) is read, at which point all pending pairs are folded in batch
-order by one kernel — running min/max for ``momentum == 0`` (reference :63-64), the EMA
+``collect`` is ONE launch per batch: the streaming reduction leaves its per-CTA partial (min, max)
+pairs in a device-side slot; nothing is folded, synchronised or copied back until
+``compute_range`` (or ``.data``) is read, at which point all pending slots are folded and merged
+in batch order by one kernel — running min/max for ``momentum == 0`` (reference :63-64), the EMA
 ``m·old + (1−m)·cur`` in float32 otherwise (reference :55-60).
 """
 from __future__ import annotations
@@ -20,14 +20,16 @@ from onnx_quantize_b200.core._calibration.base import CalibrationData, Calibrato
 
 logger = logging.getLogger(__name__)
 
-_PAIR_CHUNK = 64   # device slots for pending per-batch pairs; folded when full
+_PAIR_CHUNK = 16   # device slots for pending batches; folded when full
 
 
 class _TensorState:
     def __init__(self, device):
         self.state = torch.zeros((2,), dtype=torch.float32, device=device)
         self.valid = torch.zeros((1,), dtype=torch.int32, device=device)
-        self.pairs = torch.empty((_PAIR_CHUNK, 2), dtype=torch.float32, device=device)
+        self.slots = torch.empty((_PAIR_CHUNK, D.minmax_partials_stride(), 2), dtype=torch.float32,
+                                 device=device)
+        self.counts = torch.zeros((_PAIR_CHUNK,), dtype=torch.int32, device=device)
         self.pending = 0
 
 
@@ -71,7 +73,7 @@ class MinMaxCalibrator(Calibrator):
     # -- device side ------------------------------------------------------------------------
     def _fold(self, st: _TensorState) -> None:
         if st.pending:
-            D.minmax_merge(st.state, st.valid, st.pairs[: st.pending], self.momentum)
+            D.minmax_fold_merge(st.state, st.valid, st.slots, st.counts, st.pending, self.momentum)
             st.pending = 0
 
     def collect(self, name: str, array) -> None:
@@ -83,7 +85,7 @@ class MinMaxCalibrator(Calibrator):
             dict.__setitem__(self.data, name, CalibrationData(None, None))
         if st.pending == _PAIR_CHUNK:
             self._fold(st)
-        D.minmax_reduce(x.reshape(-1), st.pairs[st.pending])
+        D.minmax_partials(x.reshape(-1), st.slots[st.pending], st.counts[st.pending:st.pending + 1])
         st.pending += 1
 
     def device_range(self, name: str) -> torch.Tensor:

@@ -151,6 +151,21 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return v;
 }
 
+// 128-bit load that asks L2 to KEEP the line (evict_last): first pass of a two-pass algorithm whose
+// data fits the 126 MB L2, so that the second pass does not go back to HBM
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_keep4(const float* p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

@@ -26,6 +26,39 @@ __global__ void minmax_merge_kernel(float* state, int32_t* valid, const float* _
   *valid = has ? 1 : 0;
 }
 
+// All pending batches at once: fold every batch's CTA partials to its (min, max) pair, then apply
+// minmax.py:50-64 over the pairs in batch order — one single-CTA launch for any number of batches.
+// partials: [n_batches][stride] float2, counts[b] valid entries each.
+__global__ void __launch_bounds__(kMinMaxThreads) minmax_fold_merge_kernel(
+    float* state, int32_t* valid, const float2* __restrict__ partials, const int32_t* __restrict__ counts,
+    int64_t n_batches, int64_t stride, float m, float one_minus_m, int use_ema, float* __restrict__ pairs_out) {
+  __shared__ float s_lo, s_hi;
+  __shared__ int s_has;
+  if (threadIdx.x == 0) { s_lo = state[0]; s_hi = state[1]; s_has = *valid != 0; }
+  __syncthreads();
+  for (int64_t b = 0; b < n_batches; ++b) {
+    float mn = INFINITY, mx = -INFINITY;
+    const int cnt = counts[b];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const float2 p = partials[b * stride + i];
+      mn = fminf(mn, p.x); mx = fmaxf(mx, p.y);
+    }
+    block_minmax(mn, mx);
+    if (threadIdx.x == 0) {
+      if (pairs_out) { pairs_out[2 * b] = mn; pairs_out[2 * b + 1] = mx; }
+      if (!s_has) { s_lo = mn; s_hi = mx; s_has = 1; }
+      else if (use_ema) {
+        s_lo = __fadd_rn(__fmul_rn(m, s_lo), __fmul_rn(one_minus_m, mn));
+        s_hi = __fadd_rn(__fmul_rn(m, s_hi), __fmul_rn(one_minus_m, mx));
+      } else {
+        s_lo = fminf(s_lo, mn); s_hi = fmaxf(s_hi, mx);
+      }
+    }
+    __syncthreads();   // block_minmax's shared scratch is reused by the next batch
+  }
+  if (threadIdx.x == 0) { state[0] = s_lo; state[1] = s_hi; *valid = s_has; }
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -61,6 +94,32 @@ int b200q_minmax_merge(float* state, int32_t* state_valid, const float* batch_pa
   minmax_merge_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, state_valid, batch_pairs, n_batches,
                                                           (float)momentum, (float)(1.0 - momentum),
                                                           momentum > 0.0);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+size_t b200q_minmax_partials_stride(void) { return (size_t)kMinMaxMaxBlocks; }
+
+int b200q_minmax_partials(const float* x, int64_t n, void* partials, int32_t* count,
+                          b200q_stream_t stream) {
+  B200Q_REQUIRE(x && partials && count && n > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  minmax_partials_kernel<<<minmax_grid(n), kMinMaxThreads, 0, (cudaStream_t)stream>>>(x, n, (float2*)partials,
+                                                                                       count);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_minmax_fold_merge(float* state, int32_t* state_valid, const void* partials,
+                            const int32_t* counts, int64_t n_batches, double momentum,
+                            float* out_pairs, b200q_stream_t stream) {
+  B200Q_REQUIRE(state && state_valid && partials && counts && n_batches >= 0, B200Q_ERR_INVALID_ARG,
+                "bad argument");
+  B200Q_REQUIRE(momentum >= 0.0 && momentum < 1.0, B200Q_ERR_INVALID_ARG,
+                "Momentum must be in the range [0, 1).");   // minmax.py:35
+  if (n_batches == 0) return B200Q_OK;
+  minmax_fold_merge_kernel<<<1, kMinMaxThreads, 0, (cudaStream_t)stream>>>(
+      state, state_valid, (const float2*)partials, counts, n_batches, (int64_t)kMinMaxMaxBlocks,
+      (float)momentum, (float)(1.0 - momentum), momentum > 0.0, out_pairs);
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }

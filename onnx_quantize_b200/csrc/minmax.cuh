@@ -33,7 +33,10 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
 }
 
 static __global__ void __launch_bounds__(kMinMaxThreads) minmax_partials_kernel(
-    const float* __restrict__ x, int64_t n, float2* __restrict__ partials) {
+    const float* __restrict__ x, int64_t n, float2* __restrict__ partials, int32_t* __restrict__ count_out = nullptr,
+    int keep_in_l2 = 0) {
+  const uint64_t policy = l2_policy_evict_last();
+  if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = (int32_t)gridDim.x;
   float mn = INFINITY, mx = -INFINITY;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -44,22 +47,22 @@ static __global__ void __launch_bounds__(kMinMaxThreads) minmax_partials_kernel(
   const float4* x4 = reinterpret_cast<const float4*>(x + head);
   const int64_t n4 = (n - head) / 4;
   int64_t i = tid;
-  for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
-    float4 a = ldg_stream4(reinterpret_cast<const float*>(x4 + i));
-    float4 b = ldg_stream4(reinterpret_cast<const float*>(x4 + i + nthreads));
-    float4 c = ldg_stream4(reinterpret_cast<const float*>(x4 + i + 2 * nthreads));
-    float4 d = ldg_stream4(reinterpret_cast<const float*>(x4 + i + 3 * nthreads));
-    mn = fminf(fminf(fminf(mn, fminf(a.x, a.y)), fminf(a.z, a.w)),
-               fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
-    mn = fminf(fminf(fminf(mn, fminf(c.x, c.y)), fminf(c.z, c.w)),
-               fminf(fminf(d.x, d.y), fminf(d.z, d.w)));
-    mx = fmaxf(fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(a.z, a.w)),
-               fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
-    mx = fmaxf(fmaxf(fmaxf(mx, fmaxf(c.x, c.y)), fmaxf(c.z, c.w)),
-               fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w)));
+  for (; i + 7 * nthreads < n4; i += 8 * nthreads) {   // eight 128-bit loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float* src = reinterpret_cast<const float*>(x4 + i + u * nthreads);
+      v[u] = keep_in_l2 ? ldg_keep4(src, policy) : ldg_stream4(src);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      mn = fminf(fminf(fminf(mn, v[u].x), fminf(v[u].y, v[u].z)), v[u].w);
+      mx = fmaxf(fmaxf(fmaxf(mx, v[u].x), fmaxf(v[u].y, v[u].z)), v[u].w);
+    }
   }
   for (; i < n4; i += nthreads) {
-    float4 a = ldg_stream4(reinterpret_cast<const float*>(x4 + i));
+    const float* src = reinterpret_cast<const float*>(x4 + i);
+    float4 a = keep_in_l2 ? ldg_keep4(src, policy) : ldg_stream4(src);
     mn = fminf(fminf(mn, fminf(a.x, a.y)), fminf(a.z, a.w));
     mx = fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
   }
@@ -87,7 +90,7 @@ static __global__ void __launch_bounds__(kMinMaxThreads) minmax_fold_kernel(
 }
 
 inline int minmax_grid(int64_t n) {
-  int64_t per_block = (int64_t)kMinMaxThreads * 16;   // 4 x float4 per thread per sweep
+  int64_t per_block = (int64_t)kMinMaxThreads * 32;   // 8 x float4 per thread per sweep
   int64_t b = ceil_div(n, per_block);
   if (b < 1) b = 1;
   if (b > kMinMaxMaxBlocks) b = kMinMaxMaxBlocks;

@@ -298,13 +298,13 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
              ((uintptr_t)W % 16 == 0) && ((uintptr_t)out_codes % 4 == 0)) {
     // streamlined per-tensor route: min/max partials, fold + parameters, vectorised codes
     const int gsz = minmax_grid(K * N);
-    minmax_partials_kernel<<<gsz, kMinMaxThreads, 0, st>>>(W, K * N, ws.partials);
+    // weights up to 96 MB stay in L2 between the two passes (evict_last on the first read)
+    minmax_partials_kernel<<<gsz, kMinMaxThreads, 0, st>>>(W, K * N, ws.partials, nullptr,
+                                                           K * N * 4 <= (96ll << 20) ? 1 : 0);
     B200Q_LAUNCH_OK();
-    fold_qparams_tensor_kernel<<<1, 256, 0, st>>>(ws.partials, gsz, clip, qs, ws.enc_min, ws.enc_max,
-                                                  out_scale, zp_rows);
-    B200Q_LAUNCH_OK();
-    quantize_flat_kernel<<<kNumSMs * 8, 256, 0, st>>>(W, K * N / 4, qs, out_scale, zp_rows,
-                                                      (unsigned int*)out_codes);
+    quantize_flat_kernel<<<kNumSMs * 8, 256, 0, st>>>(W, K * N / 4, qs, nullptr, nullptr,
+                                                      (unsigned int*)out_codes, ws.partials, gsz, clip,
+                                                      out_scale, zp_rows, ws.enc_min, ws.enc_max);
     B200Q_LAUNCH_OK();
     return B200Q_OK;
   } else {

@@ -123,11 +123,47 @@ static __global__ void __launch_bounds__(256) fold_qparams_tensor_kernel(
 // of the array so that the tail of the preceding min/max pass is still in L2.  Codes come from the
 // reciprocal product + magic-number rounding, validated by the exact residual and redone with the
 // IEEE division when a rounding tie cannot be excluded (see rtn_stream.cuh).
+// With `partials` the kernel derives the parameters itself: every CTA folds the min/max partials of
+// the preceding pass (a few KB, L2-resident) and computes A2-tail + A3 redundantly, CTA 0 publishes
+// scale / zero point — one launch less on the per-tensor route.
 static __global__ void __launch_bounds__(256) quantize_flat_kernel(
     const float* __restrict__ W, int64_t n4, QSpec qs, const float* __restrict__ scale,
-    const unsigned char* __restrict__ zp, unsigned int* __restrict__ out) {
-  const float s = *scale;
-  const int z = decode_code(*zp, qs);
+    const unsigned char* __restrict__ zp, unsigned int* __restrict__ out,
+    const float2* __restrict__ partials, int n_partials, float clip, float* __restrict__ out_scale,
+    unsigned char* __restrict__ out_zp, unsigned int* __restrict__ enc_min, unsigned int* __restrict__ enc_max) {
+  float s;
+  int z;
+  if (partials != nullptr) {
+    __shared__ float s_mn[8], s_mx[8];
+    __shared__ float s_scale;
+    __shared__ int s_z;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
+      const float2 p = partials[i];
+      mn = fminf(mn, p.x); mx = fmaxf(mx, p.y);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+      const QParam p = qparam_from_range(fminf(__fmul_rn(mn, clip), 0.0f), fmaxf(__fmul_rn(mx, clip), 0.0f), qs);
+      s_scale = p.scale; s_z = p.zp;
+      if (blockIdx.x == 0) {
+        *out_scale = p.scale; *out_zp = encode_code(p.zp, qs);
+        *enc_min = float_to_ordered(mn); *enc_max = float_to_ordered(mx);
+      }
+    }
+    __syncthreads();
+    s = s_scale; z = s_z;
+  } else {
+    s = *scale;
+    z = decode_code(*zp, qs);
+  }
   constexpr float kMagic = 12582912.0f;
   const float delta = qs.bits == 4 ? 1.9073486328125e-06f : 3.0517578125e-05f;   // 2^-19 / 2^-15
   const float thr = s * (0.5f - delta);
@@ -141,7 +177,7 @@ static __global__ void __launch_bounds__(256) quantize_flat_kernel(
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += stride) {
     const int64_t i = n4 - 1 - j;
-    const float4 x = __ldg(w4 + i);
+    const float4 x = ldg_stream4(reinterpret_cast<const float*>(w4 + i));
     const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
     const float2 u01 = __fadd2_rn(__fmul2_rn(x01, inv2), c2), u23 = __fadd2_rn(__fmul2_rn(x23, inv2), c2);
     const float2 e01 = __ffma2_rn(__fadd2_rn(u01, nc2), ns2, x01);

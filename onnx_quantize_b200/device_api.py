@@ -318,3 +318,27 @@ def minmax_merge(state: torch.Tensor, valid: torch.Tensor, pairs: torch.Tensor, 
     rc = lib.b200q_minmax_merge(state.data_ptr(), valid.data_ptr(), pairs.data_ptr(),
                                 pairs.numel() // 2, float(momentum), dev.stream_ptr())
     _lib.check(rc, "b200q_minmax_merge")
+
+
+def minmax_partials_stride() -> int:
+    """float2 entries per batch slot of ``minmax_partials``."""
+    return int(_lib.load().b200q_minmax_partials_stride())
+
+
+def minmax_partials(x: torch.Tensor, slot: torch.Tensor, count: torch.Tensor) -> None:
+    """Per-CTA partial (min, max) pairs of one batch into ``slot`` (f32 (stride, 2)); the number of
+    valid pairs into the device int32 ``count``.  One launch, no fold (see ``minmax_fold_merge``)."""
+    lib = _lib.load()
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise ValueError("activation must be a contiguous float32 CUDA tensor")
+    _lib.check(lib.b200q_minmax_partials(x.data_ptr(), x.numel(), slot.data_ptr(), count.data_ptr(),
+                                         dev.stream_ptr()), "b200q_minmax_partials")
+
+
+def minmax_fold_merge(state: torch.Tensor, valid: torch.Tensor, slots: torch.Tensor, counts: torch.Tensor,
+                      n_batches: int, momentum: float, out_pairs: torch.Tensor | None = None) -> None:
+    """Fold ``n_batches`` slots and apply the running min/max (or EMA) update in batch order."""
+    lib = _lib.load()
+    _lib.check(lib.b200q_minmax_fold_merge(state.data_ptr(), valid.data_ptr(), slots.data_ptr(),
+                                           counts.data_ptr(), int(n_batches), float(momentum),
+                                           dev.ptr(out_pairs), dev.stream_ptr()), "b200q_minmax_fold_merge")
