@@ -392,6 +392,24 @@ def run_small_variants(torch, device, peak):
         "roofline": {"bound": "hbm", "kernel": "minmax_partials_kernel", "achieved": 4.0 * elts / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": 4.0 * elts / (ms * 1e-3) / 1e9 / peak,
                      "algorithmic_bytes_per_element": 4.0}}
+    # N3: AWQ scale + clip search (30 candidates) for one q_proj-shaped weight, statistics given
+    from onnx_quantize_b200 import awq as A
+    k = 4096
+    st = A.AwqStatistics(k)
+    xa = torch.randn((8192, k), generator=gen, device=device) * (torch.rand((k,), generator=gen, device=device) * 2 + 0.2)
+    ms_stats = time_ms(lambda: st.add(xa), iters=3, warm=1)
+    wq = ws[0]
+    ms = time_ms(lambda: A.awq_search(wq, st, QuantType.QUInt4, "group", 128, False, False, clip_search=True),
+                 iters=2, warm=1)
+    flops = 30 * 2.0 * k * k * wq.shape[1] * 3          # 30 Gram products, 3xTF32
+    out["awq_uint4_g128_q_proj"] = {
+        "workload": "AWQ scale grid (20) + clip grid (10) for one 4096x4096 weight, uint4 g128, through the Gram "
+                    "matrix (pre_passes/awq.py:121-184, :207-254); statistics accumulation timed separately",
+        "ms_per_step": ms, "stats_ms_per_8192_tokens": ms_stats,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tn_tc_kernel", "achieved": flops / (ms * 1e-3) / 1e12,
+                     "unit": "TFLOP/s", "peak": 696.95, "frac": flops / (ms * 1e-3) / 1e12 / 696.95,
+                     "note": "tf32 MMA flops of the 30 (K,K)x(K,N) products / whole search time (the search also "
+                             "runs 30 RTN parameter passes, residual and dot kernels)"}}
     del flush
     return out
 

@@ -252,6 +252,28 @@ int b200q_gptq_quantize(const float* W, int64_t K, int64_t N, const float* U, co
                         float* out_scale, void* out_zp, float* out_deq, void* workspace,
                         size_t workspace_bytes, b200q_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * AWQ scale / clip search — the numeric core of the reference's AWQ pre-pass
+ * (pre_passes/awq.py), a caller of `_rtn_quantize` and `_dequantize_array`.
+ *   b200q_awq_abs_sum       acc[k] += sum_t |X[t][k]| — `_compute_activation_scale` (awq.py:47-50)
+ *                           before the division by the number of tokens; X is (T,K).
+ *   b200q_awq_weight_scale  out[k] = mean_n |W[k][n]| / max|W| over the parameter row of (k,n) —
+ *                           `_compute_weight_scale` (awq.py:52-70).
+ *   b200q_awq_loss          *loss_out = || X W - X W_hat ||_F^2 / (tokens * N) for one candidate,
+ *                           W_hat = dequant(RTN(W * row_scale)) / row_scale (awq.py:143-178) or, with
+ *                           row_scale == NULL, dequant(RTN(W, clip_ratio)) (awq.py:223-248).  The
+ *                           products with X are replaced by ONE product with the Gram matrix
+ *                           gram = X^T X (K,K) = (num_samples / 2) * H of b200q_hessian_accumulate.
+ * ------------------------------------------------------------------------------------------ */
+size_t b200q_awq_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t group_size);
+int b200q_awq_abs_sum(const float* X, int64_t T, int64_t K, float* acc, b200q_stream_t stream);
+int b200q_awq_weight_scale(const float* W, int64_t K, int64_t N, int strategy, int64_t group_size,
+                           float* out, void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale, const float* gram,
+                   double tokens, int qtype, int strategy, int64_t group_size, int symmetric,
+                   int reduce_range, double clip_ratio, int precision, double* loss_out, void* workspace,
+                   size_t workspace_bytes, b200q_stream_t stream);
+
 /* D (M,N; ldd) <- [D +] alpha * A^T B, A (T,M; lda), B (T,N; ldb) row-major f32: the dense product
  * of the GPTQ path (Cholesky panels, triangular inverse, block propagation gptq.py:208), exported
  * for tests.  accumulate: 0 overwrite / 1 add; precision: enum b200q_precision. */

@@ -24,6 +24,7 @@ OPTIONAL = {
     "gemm_tn_tc.cu": [],
     "linalg.cu": [],
     "gptq.cu": ["-fmad=false"],
+    "awq.cu": ["-fmad=false"],
 }
 
 COMMON = [

@@ -451,3 +451,65 @@ def layer_output_rel_mse(x, w, w_hat) -> float:
     x = np.reshape(x, (-1, x.shape[-1])).astype(np.float64)
     num = np.linalg.norm(x @ (w_hat.astype(np.float64) - w.astype(np.float64))) ** 2
     return float(num / np.linalg.norm(x @ w.astype(np.float64)) ** 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# AWQ scale / clip search — reference: pre_passes/awq.py:47-70 (scales), :114-184 (scale grid),
+# :207-254 (clip grid).  Pinned live against the reference's AwqPass driven through
+# oracle/ref_shim.py::run_reference_awq (tests/test_oracle_golden.py).
+# ----------------------------------------------------------------------------------------------
+def awq_activation_scale(x):
+    """mean |x| per input channel over all tokens (awq.py:47-50)."""
+    return np.mean(np.reshape(np.abs(x), (-1, x.shape[-1])), axis=0)
+
+
+def awq_weight_scale(w, strategy: str, group_size: int):
+    """mean over output channels of |w| / max|w| of its parameter row (awq.py:52-70); w is (K,N)."""
+    wt = w.T
+    shape = wt.shape
+    rows = np.reshape(wt, (-1, group_size)) if strategy == "group" else wt
+    if strategy == "tensor":
+        s = np.abs(rows) / np.max(np.abs(rows))
+    else:
+        s = np.abs(rows) / np.max(np.abs(rows), axis=1, keepdims=True)
+    return np.mean(np.reshape(s, shape), axis=0)
+
+
+def awq_fake_quant(w, qtype, strategy, group_size, symmetric, reduce_range, clip_ratio=1.0):
+    q, s, z = rtn_quantize(w, qtype, strategy, group_size, symmetric, reduce_range, clip_ratio, False)
+    return dequantize_weight(q, s, z, strategy, group_size)
+
+
+def awq_scale_search(w, x, qtype, strategy, group_size, symmetric=False, reduce_range=False, n_grid=20):
+    """→ (best per-input-channel scale (K,), losses (n_grid,)) — awq.py:121-184."""
+    act = awq_activation_scale(x)
+    ws = awq_weight_scale(w, strategy, group_size)
+    ref_out = np.matmul(x, w)
+    best, best_scale, losses = np.inf, None, []
+    for i in range(n_grid):
+        ratio = i * 1 / n_grid
+        scale = np.clip(np.power(act, ratio) / np.power(ws, (1 - ratio)), 1e-4, None)
+        scale = scale / np.sqrt(np.max(scale) * np.min(scale))
+        col = scale.reshape(-1, 1)
+        wq = awq_fake_quant(w * col, qtype, strategy, group_size, symmetric, reduce_range) / col
+        diff = (ref_out - np.matmul(x, wq)).ravel()
+        loss = float(diff @ diff) / diff.size
+        losses.append(loss)
+        if loss < best:
+            best, best_scale = loss, scale
+    return best_scale, np.array(losses)
+
+
+def awq_clip_search(w, x, qtype, strategy, group_size, symmetric=False, reduce_range=False):
+    """→ (best clip ratio, losses (10,)) — awq.py:207-254."""
+    ref_out = np.matmul(x, w)
+    best, best_ratio, losses = np.inf, 1, []
+    for i in range(10):
+        ratio = 1 - i / 100
+        wq = awq_fake_quant(w, qtype, strategy, group_size, symmetric, reduce_range, ratio)
+        diff = (ref_out - np.matmul(x, wq)).ravel()
+        loss = float(diff @ diff) / diff.size
+        losses.append(loss)
+        if loss < best:
+            best, best_ratio = loss, ratio
+    return best_ratio, np.array(losses)

@@ -84,6 +84,15 @@ def _install_onnx_ir_stub() -> None:
     ir.tape.Tape = object
     ir.passes = types.ModuleType("onnx_ir.passes")
     ir.passes.InPlacePass = object
+    ir.passes.PassResult = lambda model, modified=False: (model, modified)
+    ir.Node = object
+    ir.Model = object
+    ir.convenience = types.ModuleType("onnx_ir.convenience")
+    ir.convenience.get_const_tensor = lambda v: getattr(v, "const_value", None)
+    # the node keeps its Value object: carrying the new tensor over is what "replace all uses" means here
+    ir.convenience.replace_all_uses_with = lambda old, new: setattr(old, "const_value", new.const_value)
+    ir.AttrInt64 = lambda name, value: types.SimpleNamespace(as_int=lambda: value)
+    sys.modules["onnx_ir.convenience"] = ir.convenience
     sys.modules["onnx_ir"] = ir
     sys.modules["onnx_ir.tape"] = ir.tape
     sys.modules["onnx_ir.passes"] = ir.passes
@@ -132,3 +141,33 @@ def load():
     ns.QWeightArgs = ns.qconfig.QWeightArgs
     _loaded = ns
     return ns
+
+
+def run_reference_awq(w, x, qconfig_kwargs: dict, clip_search: bool = False):
+    """Run the reference's ``AwqPass._apply_awq`` (and ``_apply_awq_clip``) — unmodified, executed
+    where it lies — on a stand-in MatMul node holding weight ``w`` (K,N) and calibration input
+    ``x``.  Returns ``(best_scale (K,), best_clip_ratio or None)``."""
+    import numpy as np
+
+    r = load()
+    _namespace("onnx_quantize.pre_passes", os.path.join(_SRC, "pre_passes"))
+    awq = importlib.import_module("onnx_quantize.pre_passes.awq")
+    ir = sys.modules["onnx_ir"]
+    qconfig = r.QConfig(**qconfig_kwargs)
+    w_val = ir.val("w", const_value=ir.tensor(np.array(w, copy=True)))
+    node = types.SimpleNamespace(
+        op_type="MatMul", domain="", inputs=[ir.val("x"), w_val], attributes={},
+        outputs=[types.SimpleNamespace(name="y")],
+        meta={"qconfig": qconfig.model_dump(), "input": np.array(x, copy=True)})
+    model = types.SimpleNamespace(graph=types.SimpleNamespace(initializers={}))
+    p = awq.AwqPass(clip_search=clip_search, target_op_types=("MatMul", "Gemm"))
+    captured = {}
+    p._insert_mul_node_before = lambda n, m, scale_init: captured.__setitem__("inv", scale_init.const_value.numpy())
+    assert p._apply_awq(node, model)
+    best_scale = 1.0 / captured["inv"]
+    best_clip = None
+    if clip_search:
+        # runs on the node as _apply_awq left it: weights scaled by best_scale, inputs divided by it
+        assert p._apply_awq_clip(node)
+        best_clip = r.QConfig(**node.meta["qconfig"]).weights.clip_ratio
+    return best_scale, best_clip
