@@ -414,6 +414,63 @@ def run_small_variants(torch, device, peak):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# cfg3 end to end: static W8A8 of a synthetic Gemm MLP, calibration forward on the device, batches
+# sharded over the ranks, activation ranges combined with one NCCL min/max all-reduce
+# ------------------------------------------------------------------------------------------------
+def run_cfg3_mlp(torch, dist, device, world, rank):
+    import onnx_quantize_b200 as q
+    from onnx_quantize_b200 import device_api as D
+    from onnx_quantize_b200.calibrate_mlp import DenseLayer, calibrate_mlp
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(7)                                   # identical model and data on every rank
+    k = 4096
+    layers = [DenseLayer(f"fc{i}", torch.randn((k, k), generator=gen, device=device) * 0.02,
+                         torch.randn((k,), generator=gen, device=device) * 0.1, "relu" if i == 0 else None)
+              for i in range(2)]
+    data = torch.randn((100, 512, k), generator=gen, device=device)
+    cfg = q.QConfig(weights=q.QWeightArgs(dtype="int8", symmetric=True, strategy="channel"),
+                    input_activations=q.QActivationArgs(dtype="uint8", is_static=True),
+                    output_activations=q.QActivationArgs(dtype="uint8", is_static=True),
+                    calibration_params=q.CalibrationParams(num_samples=100, batch_size=10))
+
+    def step():
+        acts = calibrate_mlp(layers, data, cfg)
+        outs = []
+        for l in layers:                                  # weights: RTN int8 per-channel; bias: int32 (A9)
+            _, ws, _ = wq = D.rtn_quantize(l.weight, q.QuantType.QInt8, "channel", -1, True)
+            outs.append((wq, D.quantize_bias(l.bias, float(acts[l.name]["input_scale"]), ws)))
+        return acts, outs
+
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    step()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    del data, layers
+    torch.cuda.empty_cache()
+    return {"workload": "cfg3: static W8A8 of a 2-layer 4096-wide Gemm MLP, 100x512x4096 f32 calibration samples in 10 "
+                        f"batches sharded over {world} rank(s): on-device forward (tcgen05 3xTF32), min/max of 4 "
+                        "activation tensors, NCCL min/max all-reduce, uint8 activation parameters, int8 per-channel "
+                        "weights, int32 biases", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
+            "calibration_bytes": 100 * 512 * k * 4, "value": 100 * 512 * k * 4 / (ms * 1e-3) / 1e9, "unit": "GB/s",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_tc_kernel", "unit": "TFLOP/s",
+                         "achieved": 2 * 2.0 * 51200 * k * k * 3 / world / (ms * 1e-3) / 1e12, "peak": 696.95,
+                         "frac": 2 * 2.0 * 51200 * k * k * 3 / world / (ms * 1e-3) / 1e12 / 696.95,
+                         "note": "tf32 MMA flops of the two forward products per GPU / whole step"}}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -508,6 +565,9 @@ def run_gpu_arm(args):
                "api": "onnx_quantize_b200.pipeline.quantize_weights_bulk (pinned host weights in, host results out)"}
 
     small = run_small_variants(torch, device, measured_peaks()[0]) if rank == 0 else None
+    cfg3 = run_cfg3_mlp(torch, dist, device, world, rank)
+    if small is not None:
+        small["cfg3_static_w8a8_mlp"] = cfg3
     gptq = None
     if not args.no_gptq:
         del plans, weights

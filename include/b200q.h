@@ -274,6 +274,14 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
                    int reduce_range, double clip_ratio, int precision, double* loss_out, void* workspace,
                    size_t workspace_bytes, b200q_stream_t stream);
 
+/* On-device calibration forward for MatMul / Gemm (+Relu) chains — what the reference gets from an
+ * ONNX Runtime session (core/_calibration/calibrate.py:204-251).  Activations stay feature-major
+ * (K x tokens) so that every layer is a b200q_gemm_tn: Y^T = gemm_tn(W, X^T).
+ *   b200q_transpose  out (cols x rows) = in (rows x cols)^T — the calibration batch into that layout
+ *   b200q_bias_act   Y (N x T) <- act(Y + bias[n]); bias may be NULL; relu 0/1 */
+int b200q_transpose(const float* in, int64_t rows, int64_t cols, float* out, b200q_stream_t stream);
+int b200q_bias_act(float* Y, int64_t N, int64_t T, const float* bias, int relu, b200q_stream_t stream);
+
 /* D (M,N; ldd) <- [D +] alpha * A^T B, A (T,M; lda), B (T,N; ldb) row-major f32: the dense product
  * of the GPTQ path (Cholesky panels, triangular inverse, block propagation gptq.py:208), exported
  * for tests.  accumulate: 0 overwrite / 1 add; precision: enum b200q_precision. */
