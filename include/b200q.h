@@ -274,6 +274,17 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
                    int reduce_range, double clip_ratio, int precision, double* loss_out, void* workspace,
                    size_t workspace_bytes, b200q_stream_t stream);
 
+/* SmoothQuant scale migration — the numerics of pre_passes/smooth_quant.py:
+ *   b200q_col_abs_max  acc[k] = max(acc[k], max_t |X[t][k]|) — `_compute_activation_scale` (:62-69)
+ *                      before the 1e-5 floor; acc must start at 0
+ *   b200q_row_abs_max  out[k] = max_n |W[k][n]| — `_compute_weight_scale` (:71-74)
+ *   b200q_scale_rows   out[k][n] = W[k][n] * row_scale[k] — fusing the scale into the weights
+ *                      (:116; also awq.py:152,181) */
+int b200q_col_abs_max(const float* X, int64_t T, int64_t K, float* acc, b200q_stream_t stream);
+int b200q_row_abs_max(const float* W, int64_t K, int64_t N, float* out, b200q_stream_t stream);
+int b200q_scale_rows(const float* W, int64_t K, int64_t N, const float* row_scale, float* out,
+                     b200q_stream_t stream);
+
 /* On-device calibration forward for MatMul / Gemm (+Relu) chains — what the reference gets from an
  * ONNX Runtime session (core/_calibration/calibrate.py:204-251).  Activations stay feature-major
  * (K x tokens) so that every layer is a b200q_gemm_tn: Y^T = gemm_tn(W, X^T).

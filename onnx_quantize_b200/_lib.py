@@ -87,6 +87,9 @@ _OPTIONAL_SIGNATURES = {
     "b200q_awq_weight_scale": (_i32, [_ptr, _i64, _i64, _i32, _i64, _ptr, _ptr, _sz, _ptr]),
     "b200q_awq_loss": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _f64, _i32, _i32, _i64, _i32, _i32, _f64, _i32,
                                _ptr, _ptr, _sz, _ptr]),
+    "b200q_col_abs_max": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
+    "b200q_row_abs_max": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
+    "b200q_scale_rows": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _ptr]),
     "b200q_transpose": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
     "b200q_bias_act": (_i32, [_ptr, _i64, _i64, _ptr, _i32, _ptr]),
     "b200q_gemm_tn": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _f32, _i32, _i32,

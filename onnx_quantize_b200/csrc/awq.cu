@@ -57,6 +57,43 @@ __global__ void __launch_bounds__(256) awq_weight_scale_kernel(const float* __re
   }
 }
 
+// acc[k] = max(acc[k], max_t |X[t][k]|) — SmoothQuant's activation scale (smooth_quant.py:62-66);
+// non-negative floats order like their bit patterns, so the fold is an integer atomicMax
+__global__ void __launch_bounds__(256) col_abs_max_kernel(const float* __restrict__ X, int64_t T, int64_t K,
+                                                          float* __restrict__ acc) {
+  __shared__ float part[8][33];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int64_t k = (int64_t)blockIdx.x * 32 + c;
+  const int64_t t0 = (int64_t)blockIdx.y * 2048, t1 = min(t0 + 2048, T);
+  float m = 0.f;
+  if (k < K)
+    for (int64_t t = t0 + r; t < t1; t += 8) m = fmaxf(m, fabsf(__ldg(X + t * K + k)));
+  part[r][c] = m;
+  __syncthreads();
+  if (r == 0 && k < K) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, part[w][c]);
+    atomicMax(reinterpret_cast<int*>(acc + k), __float_as_int(m));
+  }
+}
+
+// out[k] = max_n |W[k][n]|   (smooth_quant.py:72: np.max(np.abs(weights), axis=1))
+__global__ void __launch_bounds__(256) row_abs_max_kernel(const float* __restrict__ W, int64_t N,
+                                                          float* __restrict__ out) {
+  __shared__ float part[8];
+  const int64_t k = blockIdx.x;
+  float m = 0.f;
+  for (int64_t n = threadIdx.x; n < N; n += blockDim.x) m = fmaxf(m, fabsf(W[k * N + n]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, part[w]);
+    out[k] = m;
+  }
+}
+
 __global__ void awq_scale_rows_kernel(const float* __restrict__ W, int64_t K, int64_t N,
                                       const float* __restrict__ s, float* __restrict__ out) {
   const int64_t total = K * N;
@@ -132,6 +169,30 @@ int b200q_awq_abs_sum(const float* X, int64_t T, int64_t K, float* acc, b200q_st
   dim3 grid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(T, 2048));
   B200Q_REQUIRE(grid.y <= 65535, B200Q_ERR_UNSUPPORTED, "more than 134M tokens in one call");
   awq_abs_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, T, K, acc);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_col_abs_max(const float* X, int64_t T, int64_t K, float* acc, b200q_stream_t stream) {
+  B200Q_REQUIRE(X && acc && T > 0 && K > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  dim3 grid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(T, 2048));
+  B200Q_REQUIRE(grid.y <= 65535, B200Q_ERR_UNSUPPORTED, "more than 134M tokens in one call");
+  col_abs_max_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, T, K, acc);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_row_abs_max(const float* W, int64_t K, int64_t N, float* out, b200q_stream_t stream) {
+  B200Q_REQUIRE(W && out && K > 0 && N > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  row_abs_max_kernel<<<(unsigned)K, 256, 0, (cudaStream_t)stream>>>(W, N, out);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_scale_rows(const float* W, int64_t K, int64_t N, const float* row_scale, float* out,
+                     b200q_stream_t stream) {
+  B200Q_REQUIRE(W && row_scale && out && K > 0 && N > 0, B200Q_ERR_INVALID_ARG, "bad argument");
+  awq_scale_rows_kernel<<<grid_for(K * N), 256, 0, (cudaStream_t)stream>>>(W, K, N, row_scale, out);
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }

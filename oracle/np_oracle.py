@@ -513,3 +513,15 @@ def awq_clip_search(w, x, qtype, strategy, group_size, symmetric=False, reduce_r
         if loss < best:
             best, best_ratio = loss, ratio
     return best_ratio, np.array(losses)
+
+
+# ----------------------------------------------------------------------------------------------
+# SmoothQuant — reference: pre_passes/smooth_quant.py:62-74, :104-116.  Pinned live through
+# oracle/ref_shim.py::run_reference_smooth_quant.
+# ----------------------------------------------------------------------------------------------
+def smooth_quant(w, x, alpha: float = 0.5):
+    """→ (scale (K,), updated weights (K,N)); the layer input is divided by ``scale``."""
+    act = np.maximum(np.max(np.abs(x.reshape(-1, x.shape[-1])), axis=0), 1e-5)
+    wmax = np.max(np.abs(w), axis=1)
+    scale = np.power(act, alpha) / np.power(wmax + 1e-9, (1 - alpha))
+    return scale, np.multiply(scale.reshape(-1, 1), w)

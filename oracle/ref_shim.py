@@ -171,3 +171,25 @@ def run_reference_awq(w, x, qconfig_kwargs: dict, clip_search: bool = False):
         assert p._apply_awq_clip(node)
         best_clip = r.QConfig(**node.meta["qconfig"]).weights.clip_ratio
     return best_scale, best_clip
+
+
+def run_reference_smooth_quant(w, x, alpha: float = 0.5):
+    """The reference's ``SmoothQuantPass._smooth_quant_node`` on a stand-in MatMul node →
+    ``(scale (K,), updated weights)``."""
+    import numpy as np
+
+    r = load()
+    _namespace("onnx_quantize.pre_passes", os.path.join(_SRC, "pre_passes"))
+    sq = importlib.import_module("onnx_quantize.pre_passes.smooth_quant")
+    ir = sys.modules["onnx_ir"]
+    qconfig = r.QConfig(weights=dict(dtype="int8"), preprocessors=[dict(preprocessing_type="smooth_quant", alpha=alpha)])
+    w_val = ir.val("w", const_value=ir.tensor(np.array(w, copy=True)))
+    node = types.SimpleNamespace(op_type="MatMul", domain="", inputs=[ir.val("x"), w_val], attributes={},
+                                 outputs=[types.SimpleNamespace(name="y")],
+                                 meta={"qconfig": qconfig.model_dump(), "input": np.array(x, copy=True)})
+    model = types.SimpleNamespace(graph=types.SimpleNamespace(initializers={}))
+    p = sq.SmoothQuantPass(alpha=alpha, target_op_types=("MatMul", "Gemm"))
+    captured = {}
+    p._insert_mul_node_before = lambda n, m, scale_init: captured.__setitem__("inv", scale_init.const_value.numpy())
+    assert p._smooth_quant_node(node, model)
+    return 1.0 / captured["inv"], model.graph.initializers["w"].const_value.numpy()

@@ -65,3 +65,24 @@ def test_scale_and_clip_search_match_oracle(cuda, precision, qt, strategy, gs, s
         assert j_got == j_ref or abs(cl_ref[j_got] - cl_ref[j_ref]) <= 2e-3 * cl_ref[j_ref]
         if j_got == j_ref:
             assert res.best_clip_ratio == c_ref
+
+
+@pytest.mark.parametrize("alpha", [0.5, 0.8])
+def test_smooth_quant_matches_oracle(cuda, alpha):
+    """SmoothQuant scale migration (onnx_quantize_b200/smooth_quant.py): max|x| streamed in batches,
+    max|w| per input channel, scale and fused weights to pow()'s last bit of the oracle."""
+    from onnx_quantize_b200.smooth_quant import SmoothQuantStatistics, smooth_quant
+    rng = np.random.default_rng(4)
+    k, n = 320, 136
+    w = (rng.standard_normal((k, n)) * 0.05).astype(np.float32)
+    x = (rng.standard_normal((9, 33, k)) * rng.uniform(0.1, 4, k)).astype(np.float32)
+    x[..., 11] = 0.0
+    st = SmoothQuantStatistics(k)
+    for b in np.array_split(x, 4):
+        st.add(b)
+    assert np.array_equal(st.abs_max.cpu().numpy(), np.max(np.abs(x.reshape(-1, k)), axis=0))
+    s, w2 = smooth_quant(w, st, alpha)
+    s_ref, w_ref = O.smooth_quant(w, x, alpha)
+    np.testing.assert_allclose(s, s_ref, rtol=1e-6)
+    np.testing.assert_allclose(w2, w_ref, rtol=1e-6)
+    assert np.array_equal(w2, (s.reshape(-1, 1) * w).astype(np.float32))      # the fusion itself is exact
