@@ -5,6 +5,8 @@ libb200quant.so.  Every helper raises when no CUDA device is available — there
 """
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
 import torch
 
@@ -43,6 +45,22 @@ def to_device_f32(x, *, name: str = "array") -> torch.Tensor:
     if t.device.type != "cuda":
         t = t.to(dev, non_blocking=True)
     return t.contiguous()
+
+
+@contextlib.contextmanager
+def inputs_resident(on: bool = True):
+    """Within the context the caller asserts that every input tensor handed to the library was
+    complete before the previous kernel on the current stream was enqueued (weights / calibration
+    batches already in HBM), so input-only kernels may overlap that kernel's tail — see
+    ``b200q_assume_inputs_resident`` in include/b200q.h."""
+    from onnx_quantize_b200 import _lib
+
+    lib = _lib.load()
+    prev = lib.b200q_assume_inputs_resident(int(bool(on)))
+    try:
+        yield
+    finally:
+        lib.b200q_assume_inputs_resident(prev)
 
 
 _WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "b200q_status_string": (ctypes.c_char_p, [_i32]),
     "b200q_last_error": (ctypes.c_char_p, []),
     "b200q_launch_count": (ctypes.c_longlong, []),
+    "b200q_assume_inputs_resident": (_i32, [_i32]),
     "b200q_rtn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i32]),
     "b200q_rtn_quantize": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _f64, _i32, _i32,
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
@@ -70,7 +71,7 @@ _SIGNATURES = {
     "b200q_minmax_merge": (_i32, [_ptr, _ptr, _ptr, _i64, _f64, _ptr]),
     "b200q_minmax_partials_stride": (_sz, []),
     "b200q_minmax_partials": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr]),
-    "b200q_minmax_fold_merge": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _f64, _ptr, _ptr]),
+    "b200q_minmax_fold_merge": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr]),
 }
 _OPTIONAL_SIGNATURES = {
     "b200q_hessian_workspace_bytes": (_sz, [_i64, _i64, _i32]),

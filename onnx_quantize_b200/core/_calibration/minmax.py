@@ -76,8 +76,13 @@ class MinMaxCalibrator(Calibrator):
             D.minmax_fold_merge(st.state, st.valid, st.slots, st.counts, st.pending, self.momentum)
             st.pending = 0
 
-    def collect(self, name: str, array) -> None:
-        """Fold one activation batch (numpy array or CUDA tensor) into the statistics of ``name``."""
+    def collect(self, name: str, array, *, resident: bool = False) -> None:
+        """Fold one activation batch (numpy array or CUDA tensor) into the statistics of ``name``.
+
+        ``resident=True`` (an extension; the reference has no such argument) asserts that ``array``
+        is a CUDA tensor whose contents were complete before the previous kernel on the current
+        stream was enqueued — e.g. calibration batches already in HBM — so the reduction may overlap
+        the tail of that kernel (programmatic dependent launch, ``b200q_assume_inputs_resident``)."""
         x = dev.to_device_f32(array)
         st = self._dev.get(name)
         if st is None:
@@ -85,7 +90,8 @@ class MinMaxCalibrator(Calibrator):
             dict.__setitem__(self.data, name, CalibrationData(None, None))
         if st.pending == _PAIR_CHUNK:
             self._fold(st)
-        D.minmax_partials(x.reshape(-1), st.slots[st.pending], st.counts[st.pending:st.pending + 1])
+        with dev.inputs_resident(resident and x is array):
+            D.minmax_partials(x.reshape(-1), st.slots[st.pending], st.counts[st.pending:st.pending + 1])
         st.pending += 1
 
     def device_range(self, name: str) -> torch.Tensor:

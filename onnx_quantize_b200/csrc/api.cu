@@ -11,7 +11,10 @@ namespace b200q {
 static thread_local char g_last_error[512] = "";
 static std::atomic<long long> g_launches{0};
 
+static thread_local int g_inputs_resident = 0;
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool inputs_resident() { return g_inputs_resident != 0; }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -79,6 +82,12 @@ const char* b200q_status_string(int status) {
 }
 
 const char* b200q_last_error(void) { return b200q::g_last_error; }
+
+int b200q_assume_inputs_resident(int on) {
+  const int prev = b200q::g_inputs_resident;
+  b200q::g_inputs_resident = on ? 1 : 0;
+  return prev;
+}
 
 long long b200q_launch_count(void) { return b200q::g_launches.load(std::memory_order_relaxed); }
 

@@ -221,7 +221,7 @@ int b200q_awq_weight_scale(const float* W, int64_t K, int64_t N, int strategy, i
   float2* partials = (float2*)(enc_max + align_up((size_t)rows * 4, 256) / 4);   // inside the K*N*4 areas
   if (strategy == B200Q_TENSOR) {
     const int g = minmax_grid(K * N);
-    minmax_partials_kernel<<<g, kMinMaxThreads, 0, st>>>(W, K * N, partials);
+    launch_minmax_partials(W, K * N, partials, nullptr, 0, false, g, st);
     B200Q_LAUNCH_OK();
     minmax_fold_kernel<<<1, kMinMaxThreads, 0, st>>>(partials, g, nullptr, enc_min, enc_max);
   } else {

@@ -19,6 +19,7 @@ namespace b200q {
 
 void set_last_error(const char* fmt, ...);
 void count_launch();   // bumps the process-wide kernel-launch counter (b200q_launch_count)
+bool inputs_resident();   // thread-local hint set by b200q_assume_inputs_resident
 
 #define B200Q_REQUIRE(cond, code, ...)          \
   do {                                          \
@@ -164,6 +165,38 @@ __device__ __forceinline__ float4 ldg_keep4(const float* p, uint64_t policy) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p), "l"(policy));
   return v;
+}
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// launch_dependents: the next kernel on the stream — if it was launched with the programmatic
+// stream-serialization attribute — may be scheduled once every CTA of this grid has executed it.
+// wait: blocks until the previous grid on the stream has completed and its writes are visible.
+// Both are no-ops when the respective launch does not carry the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// kernel<<<grid, block, 0, st>>>(args...) with the attribute set when `programmatic` is true
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool programmatic,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = programmatic ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// 128-bit load that demotes the line in L2 (evict_first): the LAST read of data an earlier pass
+// pinned with evict_last, so that the next weight's pinned lines do not compete with dead ones
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -9,7 +9,7 @@
 namespace b200q {
 
 constexpr int kMinMaxThreads = 256;
-constexpr int kMinMaxMaxBlocks = kNumSMs * 8;
+constexpr int kMinMaxMaxBlocks = kNumSMs * 4;   // 4 CTAs/SM x 8 loads in flight: best of the sweep in tools/bench_stream_reduce.cu
 
 __device__ __forceinline__ void warp_minmax(float& mn, float& mx) {
 #pragma unroll
@@ -32,9 +32,22 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
   }
 }
 
-static __global__ void __launch_bounds__(kMinMaxThreads) minmax_partials_kernel(
-    const float* __restrict__ x, int64_t n, float2* __restrict__ partials, int32_t* __restrict__ count_out = nullptr,
-    int keep_in_l2 = 0) {
+// Programmatic dependent launch (PDL).  Every partials kernel lets its successor be scheduled as
+// soon as all of its own CTAs are resident (launch_dependents first thing) and, at its very end,
+// waits for its predecessor (griddepcontrol.wait: completion + flush of the previous grid), so a
+// chain of independent batches overlaps tail with ramp — measured 5.0 -> 7.5 TB/s on ten 84 MB
+// batches (tools/bench_stream_reduce.cu) — while "kernel N done" still implies "kernels < N done"
+// for whatever is launched normally afterwards.  Both instructions are no-ops unless the launch
+// carries the programmatic-stream-serialization attribute (launch_minmax_partials, overlap = true),
+// which is only done under b200q_assume_inputs_resident: the input must have been complete before
+// the PREVIOUS launch on the stream was enqueued (the kernel reads its input before it waits).
+// KEEP is a template parameter on purpose: as a run-time flag it made ptxas emit every load twice
+// under opposite predicates and reuse two destination registers — two loads in flight instead of
+// eight (found in the SASS; the kernel sat at 58 % of the roofline because of it).
+template <bool KEEP>
+static __global__ void __launch_bounds__(kMinMaxThreads, 4) minmax_partials_kernel(
+    const float* __restrict__ x, int64_t n, float2* __restrict__ partials, int32_t* __restrict__ count_out) {
+  pdl_launch_dependents();
   const uint64_t policy = l2_policy_evict_last();
   if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = (int32_t)gridDim.x;
   float mn = INFINITY, mx = -INFINITY;
@@ -52,7 +65,7 @@ static __global__ void __launch_bounds__(kMinMaxThreads) minmax_partials_kernel(
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float* src = reinterpret_cast<const float*>(x4 + i + u * nthreads);
-      v[u] = keep_in_l2 ? ldg_keep4(src, policy) : ldg_stream4(src);
+      v[u] = KEEP ? ldg_keep4(src, policy) : ldg_stream4(src);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -60,17 +73,35 @@ static __global__ void __launch_bounds__(kMinMaxThreads) minmax_partials_kernel(
       mx = fmaxf(fmaxf(fmaxf(mx, v[u].x), fmaxf(v[u].y, v[u].z)), v[u].w);
     }
   }
-  for (; i < n4; i += nthreads) {
-    const float* src = reinterpret_cast<const float*>(x4 + i);
-    float4 a = keep_in_l2 ? ldg_keep4(src, policy) : ldg_stream4(src);
-    mn = fminf(fminf(mn, fminf(a.x, a.y)), fminf(a.z, a.w));
-    mx = fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+  if (i < n4) {   // last partial sweep: predicated, still issued together
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t j = i + u * nthreads;
+      const float* src = reinterpret_cast<const float*>(x4 + (j < n4 ? j : i));
+      v[u] = KEEP ? ldg_keep4(src, policy) : ldg_stream4(src);   // out of range: re-reads chunk i (harmless)
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      mn = fminf(fminf(fminf(mn, v[u].x), fminf(v[u].y, v[u].z)), v[u].w);
+      mx = fmaxf(fmaxf(fmaxf(mx, v[u].x), fmaxf(v[u].y, v[u].z)), v[u].w);
+    }
   }
   // tail
   int64_t t = head + n4 * 4 + tid;
   if (t < n) { float v = x[t]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
   block_minmax(mn, mx);
   if (threadIdx.x == 0) partials[blockIdx.x] = make_float2(mn, mx);
+  pdl_wait();
+}
+
+// overlap = the launch may start while the previous kernel on the stream is still running (see above)
+static inline cudaError_t launch_minmax_partials(const float* x, int64_t n, float2* partials, int32_t* count_out,
+                                                 int keep_in_l2, bool overlap, int grid, cudaStream_t st) {
+  return keep_in_l2 ? launch_pdl(minmax_partials_kernel<true>, dim3((unsigned)grid), dim3(kMinMaxThreads), st,
+                                 overlap, x, n, partials, count_out)
+                    : launch_pdl(minmax_partials_kernel<false>, dim3((unsigned)grid), dim3(kMinMaxThreads), st,
+                                 overlap, x, n, partials, count_out);
 }
 
 // Single CTA: fold the partials; write {min,max} as floats and/or as order-preserving uints.

@@ -117,7 +117,7 @@ static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWor
                            cudaStream_t st) {
   if (m.strategy == B200Q_TENSOR) {
     int g = minmax_grid(m.K * m.N);
-    minmax_partials_kernel<<<g, kMinMaxThreads, 0, st>>>(W, m.K * m.N, ws.partials);
+    launch_minmax_partials(W, m.K * m.N, ws.partials, nullptr, 0, false, g, st);
     B200Q_LAUNCH_OK();
     minmax_fold_kernel<<<1, kMinMaxThreads, 0, st>>>(ws.partials, g, nullptr, ws.enc_min, ws.enc_max);
   } else {
@@ -299,12 +299,17 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     // streamlined per-tensor route: min/max partials, fold + parameters, vectorised codes
     const int gsz = minmax_grid(K * N);
     // weights up to 96 MB stay in L2 between the two passes (evict_last on the first read)
-    minmax_partials_kernel<<<gsz, kMinMaxThreads, 0, st>>>(W, K * N, ws.partials, nullptr,
-                                                           K * N * 4 <= (96ll << 20) ? 1 : 0);
+    // Both launches are programmatic (PDL): the code pass is resident and waiting when the min/max
+    // pass retires, and — under b200q_assume_inputs_resident — the min/max pass of the NEXT weight
+    // overlaps the tail of this code pass (it is released once every code CTA has consumed the
+    // partials it is about to rewrite).
+    launch_minmax_partials(W, K * N, ws.partials, nullptr, K * N * 4 <= (96ll << 20) ? 1 : 0, inputs_resident(),
+                           gsz, st);
     B200Q_LAUNCH_OK();
-    quantize_flat_kernel<<<kNumSMs * 8, 256, 0, st>>>(W, K * N / 4, qs, nullptr, nullptr,
-                                                      (unsigned int*)out_codes, ws.partials, gsz, clip,
-                                                      out_scale, zp_rows, ws.enc_min, ws.enc_max);
+    launch_pdl(quantize_flat_kernel, dim3(kNumSMs * 4), dim3(256), st, true,   // one wave: 4 CTAs/SM
+               W, K * N / 4, qs, (const float*)nullptr,
+               (const unsigned char*)nullptr, (unsigned int*)out_codes, (const float2*)ws.partials, gsz, clip,
+               out_scale, zp_rows, ws.enc_min, ws.enc_max);
     B200Q_LAUNCH_OK();
     return B200Q_OK;
   } else {

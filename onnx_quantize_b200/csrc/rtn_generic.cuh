@@ -126,13 +126,14 @@ static __global__ void __launch_bounds__(256) fold_qparams_tensor_kernel(
 // With `partials` the kernel derives the parameters itself: every CTA folds the min/max partials of
 // the preceding pass (a few KB, L2-resident) and computes A2-tail + A3 redundantly, CTA 0 publishes
 // scale / zero point — one launch less on the per-tensor route.
-static __global__ void __launch_bounds__(256) quantize_flat_kernel(
+static __global__ void __launch_bounds__(256, 4) quantize_flat_kernel(
     const float* __restrict__ W, int64_t n4, QSpec qs, const float* __restrict__ scale,
     const unsigned char* __restrict__ zp, unsigned int* __restrict__ out,
     const float2* __restrict__ partials, int n_partials, float clip, float* __restrict__ out_scale,
     unsigned char* __restrict__ out_zp, unsigned int* __restrict__ enc_min, unsigned int* __restrict__ enc_max) {
   float s;
   int z;
+  pdl_wait();   // launched programmatically behind the min/max pass: resident before that pass retires
   if (partials != nullptr) {
     __shared__ float s_mn[8], s_mx[8];
     __shared__ float s_scale;
@@ -164,6 +165,10 @@ static __global__ void __launch_bounds__(256) quantize_flat_kernel(
     s = *scale;
     z = decode_code(*zp, qs);
   }
+  // the partials have been consumed by every CTA once all have passed this point: the next
+  // weight's min/max pass (which rewrites them) may be scheduled from here on
+  pdl_launch_dependents();
+  const uint64_t demote = l2_policy_evict_first();
   constexpr float kMagic = 12582912.0f;
   const float delta = qs.bits == 4 ? 1.9073486328125e-06f : 3.0517578125e-05f;   // 2^-19 / 2^-15
   const float thr = s * (0.5f - delta);
@@ -175,9 +180,9 @@ static __global__ void __launch_bounds__(256) quantize_flat_kernel(
   const unsigned int mask = qs.bits == 4 ? 0x0F0F0F0Fu : 0xFFFFFFFFu;
   const float4* w4 = reinterpret_cast<const float4*>(W);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += stride) {
-    const int64_t i = n4 - 1 - j;
-    const float4 x = ldg_stream4(reinterpret_cast<const float*>(w4 + i));
+  // codes of one 128-bit chunk; the second pass runs back to front so that the lines the first
+  // pass read last (still in L2) are consumed first
+  auto emit = [&](int64_t i, const float4 x) {
     const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
     const float2 u01 = __fadd2_rn(__fmul2_rn(x01, inv2), c2), u23 = __fadd2_rn(__fmul2_rn(x23, inv2), c2);
     const float2 e01 = __ffma2_rn(__fadd2_rn(u01, nc2), ns2, x01);
@@ -194,6 +199,18 @@ static __global__ void __launch_bounds__(256) quantize_flat_kernel(
       b3 = (unsigned int)quant_code(x.w, s, z, qs.qmin, qs.qmax);
     }
     out[i] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410) & mask;
+  };
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; j + 3 * stride < n4; j += 4 * stride) {          // four 128-bit loads in flight per thread
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = ldg_keep4(reinterpret_cast<const float*>(w4 + (n4 - 1 - (j + u * stride))), demote);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(n4 - 1 - (j + u * stride), x[u]);
+  }
+  for (; j < n4; j += stride) {
+    const int64_t i = n4 - 1 - j;
+    emit(i, ldg_keep4(reinterpret_cast<const float*>(w4 + i), demote));
   }
 }
 

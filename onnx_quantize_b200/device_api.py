@@ -327,7 +327,8 @@ def minmax_partials_stride() -> int:
 
 def minmax_partials(x: torch.Tensor, slot: torch.Tensor, count: torch.Tensor) -> None:
     """Per-CTA partial (min, max) pairs of one batch into ``slot`` (f32 (stride, 2)); the number of
-    valid pairs into the device int32 ``count``.  One launch, no fold (see ``minmax_fold_merge``)."""
+    valid pairs into the device int32 ``count``.  One launch, no fold (see ``minmax_fold_merge``).
+    Inside ``_device.inputs_resident()`` the launch overlaps the tail of the previous kernel."""
     lib = _lib.load()
     if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
         raise ValueError("activation must be a contiguous float32 CUDA tensor")
@@ -336,9 +337,12 @@ def minmax_partials(x: torch.Tensor, slot: torch.Tensor, count: torch.Tensor) ->
 
 
 def minmax_fold_merge(state: torch.Tensor, valid: torch.Tensor, slots: torch.Tensor, counts: torch.Tensor,
-                      n_batches: int, momentum: float, out_pairs: torch.Tensor | None = None) -> None:
-    """Fold ``n_batches`` slots and apply the running min/max (or EMA) update in batch order."""
+                      n_batches: int, momentum: float, out_pairs: torch.Tensor | None = None,
+                      out_range: torch.Tensor | None = None) -> None:
+    """Fold ``n_batches`` slots and apply the running min/max (or EMA) update in batch order;
+    ``out_range`` (f32[2]) receives the range with zero included (minmax.py:84-87)."""
     lib = _lib.load()
     _lib.check(lib.b200q_minmax_fold_merge(state.data_ptr(), valid.data_ptr(), slots.data_ptr(),
                                            counts.data_ptr(), int(n_batches), float(momentum),
-                                           dev.ptr(out_pairs), dev.stream_ptr()), "b200q_minmax_fold_merge")
+                                           dev.ptr(out_pairs), dev.ptr(out_range), dev.stream_ptr()),
+               "b200q_minmax_fold_merge")
