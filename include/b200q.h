@@ -171,6 +171,12 @@ int b200q_dequantize(const void* codes, int64_t K, int64_t N, int qtype, int str
                      int64_t group_size, const float* scale, const void* zp, float* out,
                      b200q_stream_t stream);
 
+/* Same with float32 zero points, one per parameter row (HQQ: hqq.py:77 makes zp_dtype the scale
+ * dtype; `_dequantize_array` casts zp to f32 either way, utils.py:130-132). */
+int b200q_dequantize_float_zp(const void* codes, int64_t K, int64_t N, int qtype, int strategy,
+                              int64_t group_size, const float* scale, const float* zp, float* out,
+                              b200q_stream_t stream);
+
 /* int32 bias quantization — replaces `_quantize_bias` (rtn.py:112-138).
  * out_scale[i] = weight_scale[i or 0] * input_scale; out_q = clip(rint(bias/out_scale)). */
 int b200q_quantize_bias(const float* bias, int64_t n, const float* weight_scale,
@@ -285,6 +291,28 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
                    double tokens, int qtype, int strategy, int64_t group_size, int symmetric,
                    int reduce_range, double clip_ratio, int precision, double* loss_out, void* workspace,
                    size_t workspace_bytes, b200q_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HQQ — replaces `_hqq_quantize` (core/_algorithms/hqq.py:149-217): RTN parameters (clip / MSE
+ * options as in b200q_rtn_quantize), then `_optimize_zero_point` (:107-146) — `iters` proximal
+ * iterations of the zero point with the shrinkage operator `_shrink_op` (:103-104), the iterate
+ * with the smallest global mean |W - W_r| kept (strict <; the first non-improvement ends the
+ * search when early_stop != 0) — then the codes for that zero point (:166-175).
+ * uint4 / asymmetric / GROUP only (hqq.py:47-66); group_size -1 or a power of two >= 16.
+ *   out_codes      (K,N) one byte per element
+ *   out_scale      f32 per parameter row, order n*(K/gs)+g
+ *   out_zp         f32 per parameter row (HQQ zero points are floats: hqq.py:77)
+ *   out_best_iter  optional device int32: index of the returned iterate (-1: the RTN zero point)
+ *   out_errors     optional device f64[iters]: the global mean error of every iteration
+ * Parity: float32 op order and NumPy's pairwise row sums reproduced; `np.power` is evaluated in
+ * float64 and rounded once (NumPy's own result is host-dependent), so zero points agree to the
+ * last bits, not bit for bit.
+ * ------------------------------------------------------------------------------------------ */
+size_t b200q_hqq_workspace_bytes(int64_t K, int64_t N, int64_t group_size, int mse, int iters);
+int b200q_hqq_quantize(const float* W, int64_t K, int64_t N, int qtype, int64_t group_size, int reduce_range,
+                       double clip_ratio, int mse, double lp_norm, double beta, double kappa, int iters,
+                       int early_stop, void* out_codes, float* out_scale, float* out_zp, int32_t* out_best_iter,
+                       double* out_errors, void* workspace, size_t workspace_bytes, b200q_stream_t stream);
 
 /* SmoothQuant scale migration — the numerics of pre_passes/smooth_quant.py:
  *   b200q_col_abs_max  acc[k] = max(acc[k], max_t |X[t][k]|) — `_compute_activation_scale` (:62-69)

@@ -2,12 +2,13 @@
 
 Public names follow the reference package (``onnx_quantize/__init__.py``): ``QConfig``,
 ``QWeightArgs``, ``QActivationArgs``, ``QuantType``, ``QuantizationStrategy``, ``QFormat``,
-``CalibrationParams``, ``CalibrationMethod``, ``RTNConfig``, ``GPTQConfig``, ``quantize``,
+``CalibrationParams``, ``CalibrationMethod``, ``RTNConfig``, ``GPTQConfig``, ``HqqConfig``, ``quantize``,
 ``set_log_level``.  All arithmetic runs in ``lib/libb200quant.so`` (hand-written CUDA, C ABI in
 ``include/b200q.h``); there is no CPU fallback.
 """
 from onnx_quantize_b200._logging import *  # noqa: F401,F403
 from onnx_quantize_b200.core._algorithms.gptq import GPTQConfig  # noqa: F401
+from onnx_quantize_b200.core._algorithms.hqq import HqqConfig  # noqa: F401
 from onnx_quantize_b200.core._algorithms.rtn import RTNConfig  # noqa: F401
 from onnx_quantize_b200.core._calibration.base import *  # noqa: F401,F403
 from onnx_quantize_b200.core._dtypes import *  # noqa: F401,F403

@@ -88,6 +88,10 @@ _OPTIONAL_SIGNATURES = {
     "b200q_awq_weight_scale": (_i32, [_ptr, _i64, _i64, _i32, _i64, _ptr, _ptr, _sz, _ptr]),
     "b200q_awq_loss": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _f64, _i32, _i32, _i64, _i32, _i32, _f64, _i32,
                                _ptr, _ptr, _sz, _ptr]),
+    "b200q_dequantize_float_zp": (_i32, [_ptr, _i64, _i64, _i32, _i32, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "b200q_hqq_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
+    "b200q_hqq_quantize": (_i32, [_ptr, _i64, _i64, _i32, _i64, _i32, _f64, _i32, _f64, _f64, _f64, _i32, _i32,
+                                   _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "b200q_col_abs_max": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
     "b200q_row_abs_max": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
     "b200q_scale_rows": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _ptr]),

@@ -203,7 +203,12 @@ def _dequantize_array(q_array, scale, zero_point, *, preprocess=False, strategy=
     s = dev.to_device_f32(np.ascontiguousarray(np.asarray(scale, dtype=np.float32)).reshape(-1))
     if s.numel() != rows:
         s = s.expand(rows).contiguous()
-    z = _zp_to_device_bytes(zero_point, quant_type, rows)
+    if np.asarray(zero_point).dtype.kind == "f":      # HQQ: float zero points (hqq.py:77)
+        z = dev.to_device_f32(np.ascontiguousarray(np.asarray(zero_point, dtype=np.float32)).reshape(-1))
+        if z.numel() != rows:
+            z = z.expand(rows).contiguous()
+    else:
+        z = _zp_to_device_bytes(zero_point, quant_type, rows)
     out = D.dequantize(codes.contiguous(), s, z, quant_type, st, gs)
     if preprocess:
         return out.cpu().numpy()

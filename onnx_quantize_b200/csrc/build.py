@@ -25,6 +25,7 @@ OPTIONAL = {
     "linalg.cu": [],
     "gptq.cu": ["-fmad=false"],
     "awq.cu": ["-fmad=false"],
+    "hqq.cu": ["-fmad=false"],
     "mlp.cu": [],
 }
 

@@ -35,6 +35,19 @@ __global__ void dequantize_kernel(const unsigned char* __restrict__ codes, RowMa
   }
 }
 
+// float zero points (HQQ, hqq.py:77): same two float32 operations, zp read as is
+__global__ void dequantize_fzp_kernel(const unsigned char* __restrict__ codes, RowMap m, QSpec qs,
+                                      const float* __restrict__ scale, const float* __restrict__ zp,
+                                      float* __restrict__ out) {
+  int64_t total = m.K * m.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = i / m.N, n = i - k * m.N;
+    int64_t r = m.row_of(k, n);
+    out[i] = __fmul_rn(__fsub_rn((float)decode_code(codes[i], qs), zp[r]), scale[r]);
+  }
+}
+
 __global__ void quantize_bias_kernel(const float* __restrict__ bias, int64_t n,
                                      const float* __restrict__ wscale, int64_t n_wscale,
                                      float input_scale, int32_t* __restrict__ out_q,
@@ -530,6 +543,21 @@ int b200q_dequantize(const void* codes, int64_t K, int64_t N, int qtype, int str
   if (rc != B200Q_OK) return rc;
   dequantize_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
       (const unsigned char*)codes, s.map, qs, scale, (const unsigned char*)zp, out);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+int b200q_dequantize_float_zp(const void* codes, int64_t K, int64_t N, int qtype, int strategy,
+                              int64_t group_size, const float* scale, const float* zp, float* out,
+                              b200q_stream_t stream) {
+  B200Q_REQUIRE(codes && scale && zp && out, B200Q_ERR_INVALID_ARG, "null pointer argument");
+  QSpec qs;
+  B200Q_REQUIRE(make_qspec(qtype, 0, 0, &qs), B200Q_ERR_INVALID_ARG, "unknown quantization type %d", qtype);
+  Shape s;
+  int rc = resolve_shape(K, N, strategy, group_size, &s);
+  if (rc != B200Q_OK) return rc;
+  dequantize_fzp_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned char*)codes, s.map, qs, scale, zp, out);
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }

@@ -238,9 +238,9 @@ def dequantize(codes: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, quant
     lib = _lib.load()
     k, n = int(codes.shape[0]), int(codes.shape[1])
     out = torch.empty((k, n), dtype=torch.float32, device=codes.device)
-    rc = lib.b200q_dequantize(codes.data_ptr(), k, n, _qt(quant_type), _strategy(strategy),
-                              int(group_size or -1), scale.data_ptr(), zp.data_ptr(),
-                              out.data_ptr(), dev.stream_ptr())
+    fn = lib.b200q_dequantize_float_zp if zp.dtype == torch.float32 else lib.b200q_dequantize
+    rc = fn(codes.data_ptr(), k, n, _qt(quant_type), _strategy(strategy), int(group_size or -1),
+            scale.data_ptr(), zp.data_ptr(), out.data_ptr(), dev.stream_ptr())
     _lib.check(rc, "b200q_dequantize")
     return out
 

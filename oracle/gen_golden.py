@@ -207,6 +207,29 @@ def gen_gptq(r):
     print("gptq cases:", len(keys))
 
 
+HQQ_CASES = [  # (K, N, group_size, reduce_range, clip_ratio, mse, early_stop, iters, lp_norm, beta, kappa)
+    (256, 48, 64, False, 1.0, False, True, 20, 0.7, 10.0, 1.01),
+    (128, 40, 16, True, 0.9, False, False, 20, 0.7, 10.0, 1.01),
+    (512, 24, 128, False, 1.0, True, True, 20, 0.7, 10.0, 1.01),
+    (96, 8, -1, False, 1.0, False, False, 7, 0.7, 10.0, 1.01),
+    (512, 16, 256, False, 1.0, False, True, 20, 0.5, 5.0, 1.05),
+    (1024, 8, -1, False, 0.8, False, False, 12, 0.7, 10.0, 1.01),
+]
+
+
+def gen_hqq(r):
+    """`_hqq_quantize` (hqq.py:149-217) on small weights; the np.power inside is host-dependent."""
+    rng = np.random.default_rng(77)
+    blob = {"cases": np.array(json.dumps(HQQ_CASES))}
+    for i, (k, n, gs, rr, clip, mse, es, iters, lp, beta, kappa) in enumerate(HQQ_CASES):
+        w = (rng.standard_normal((k, n)) * rng.uniform(0.01, 0.1)).astype(np.float32)
+        q, s, z = r.hqq._hqq_quantize(w, r.QuantType.QUInt4, gs, rr, clip, mse, np.float32, np.float32,
+                                      lp, beta, kappa, iters, es)
+        blob[f"w::{i}"], blob[f"q::{i}"], blob[f"s::{i}"], blob[f"z::{i}"] = w, q.astype(np.uint8), s, z
+    np.savez_compressed(os.path.join(OUT, "hqq.npz"), **blob)
+    print("hqq cases:", len(HQQ_CASES))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     r = ref_shim.load()
@@ -216,6 +239,7 @@ def main():
     gen_minmax(r)
     gen_bias(r)
     gen_gptq(r)
+    gen_hqq(r)
     meta = {"numpy": np.__version__, "reference": "AyoubMDL/onnx_quantize v0.3.0",
             "power_dispatch": "host-dependent (SVML on AVX512_SKX hosts)"}
     with open(os.path.join(OUT, "META.json"), "w") as f:

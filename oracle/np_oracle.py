@@ -525,3 +525,50 @@ def smooth_quant(w, x, alpha: float = 0.5):
     wmax = np.max(np.abs(w), axis=1)
     scale = np.power(act, alpha) / np.power(wmax + 1e-9, (1 - alpha))
     return scale, np.multiply(scale.reshape(-1, 1), w)
+
+
+# ----------------------------------------------------------------------------------------------
+# HQQ — reference: core/_algorithms/hqq.py (`_shrink_op` :103-104, `_optimize_zero_point`
+# :107-146, `_hqq_quantize` :149-217).  Pinned live through tests/test_oracle_golden.py and by
+# tests/golden/hqq.npz.  uint4, asymmetric, GROUP only.
+# ----------------------------------------------------------------------------------------------
+def hqq_shrink(x, beta: float, lp_norm: float):
+    ax = np.abs(x)
+    return np.sign(x) * np.maximum(0, ax - (1.0 / beta) * np.power(ax + 1e-8, lp_norm - 1))
+
+
+def hqq_optimize_zero_point(rows, scale, zp, qmin, qmax, lp_norm=0.7, beta=1e1, kappa=1.01, iters=20,
+                            early_stop=True, return_trace=False):
+    """→ best zero point (rows,1) [, (best iteration or -1, list of global mean errors)]."""
+    best_err, best_zp, best_it = np.inf, zp.copy(), -1
+    inv = 1.0 / scale                                  # HQQ iterates with the inverted scale
+    errors = []
+    for it in range(iters):
+        w_q = np.clip(np.round(rows * inv + zp), qmin, qmax)
+        w_r = (w_q - zp) / inv
+        w_e = hqq_shrink(rows - w_r, beta, lp_norm)
+        beta *= kappa
+        err = float(np.mean(np.abs(rows - w_r)))
+        errors.append(err)
+        if err < best_err:
+            best_err, best_zp, best_it = err, zp.copy(), it
+        elif early_stop:
+            break
+        zp = np.mean(w_q - (rows - w_e) * inv, axis=1, keepdims=True)
+    if return_trace:
+        return best_zp, (best_it, errors)
+    return best_zp
+
+
+def hqq_quantize(w, group_size: int, reduce_range: bool = False, clip_ratio: float = 1.0, mse: bool = False,
+                 lp_norm=0.7, beta=1e1, kappa=1.01, iters=20, early_stop=True, return_trace=False):
+    """→ (codes (K,N) uint4, scale (N*G,1) f32, zero point (N*G,1) f32)."""
+    rows = to_rows(w, "group", group_size)
+    scale, zp = qparams_from_rows(rows, "uint4", "group", False, reduce_range, clip_ratio, mse,
+                                  zp_dtype=np.float32)
+    qmin, qmax = qrange("uint4", False, reduce_range)
+    zp, trace = hqq_optimize_zero_point(rows, scale, zp, qmin, qmax, lp_norm, beta, kappa, iters, early_stop,
+                                        return_trace=True)
+    q = np.clip(np.round(rows / scale + zp), qmin, qmax).astype(np_dtype("uint4"))
+    out = (from_rows(q, w, "group"), scale, zp)
+    return out + (trace,) if return_trace else out

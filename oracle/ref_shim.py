@@ -130,6 +130,7 @@ def load():
     ns.utils = importlib.import_module("onnx_quantize.core._algorithms.utils")
     ns.rtn = importlib.import_module("onnx_quantize.core._algorithms.rtn")
     ns.gptq = importlib.import_module("onnx_quantize.core._algorithms.gptq")
+    ns.hqq = importlib.import_module("onnx_quantize.core._algorithms.hqq")
     ns.pack = importlib.import_module("onnx_quantize.core._pack")
     ns.minmax = importlib.import_module("onnx_quantize.core._calibration.minmax")
     ns.calib_base = importlib.import_module("onnx_quantize.core._calibration.base")
