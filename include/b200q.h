@@ -68,7 +68,7 @@ enum b200q_layout { B200Q_KN_BYTES = 0, B200Q_PACKED_FLAT = 1, B200Q_MATMUL_NBIT
  * the reference's result. */
 enum b200q_mse_mode { B200Q_MSE_OFF = 0, B200Q_MSE_ON = 1, B200Q_MSE_EXACT = 2 };
 
-enum b200q_precision { B200Q_TF32 = 0, B200Q_TF32X3 = 1, B200Q_FP32_SIMT = 2 };
+enum b200q_precision { B200Q_TF32 = 0, B200Q_TF32X3 = 1, B200Q_FP32_SIMT = 2, B200Q_BF16X3 = 3 };
 
 /* GPTQ update rule: REFERENCE reproduces gptq.py:198-208 as written (reads the zero triangle of
  * the upper factor: no error propagation); PROPAGATE is GPTQ as published. */

@@ -19,7 +19,7 @@ NOT_POSITIVE_DEFINITE = 1
 QTYPE = {"int4": 0, "uint4": 1, "int8": 2, "uint8": 3}
 STRATEGY = {"tensor": 0, "channel": 1, "group": 2}
 LAYOUT = {"kn": 0, "packed_flat": 1, "matmul_nbits": 2}
-PRECISION = {"tf32": 0, "tf32x3": 1, "fp32": 2}
+PRECISION = {"tf32": 0, "tf32x3": 1, "fp32": 2, "bf16x3": 3}
 GPTQ_MODE = {"reference": 0, "propagate": 1}
 
 

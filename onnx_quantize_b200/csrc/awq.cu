@@ -240,6 +240,7 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
                    double tokens, int qtype, int strategy, int64_t group_size, int symmetric,
                    int reduce_range, double clip_ratio, int precision, double* loss_out, void* workspace,
                    size_t workspace_bytes, b200q_stream_t stream) {
+  if (precision == B200Q_BF16X3) precision = B200Q_TF32X3;   // BF16x3 is a Hessian-only mode; dense solves use TF32x3
   cudaStream_t st = (cudaStream_t)stream;
   B200Q_REQUIRE(W && gram && loss_out && K > 0 && N > 0 && tokens > 0, B200Q_ERR_INVALID_ARG, "bad argument");
   QSpec qs;

@@ -83,6 +83,7 @@ int gemm_tn(const GemmTN& g, cudaStream_t st) {
 extern "C" int b200q_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D,
                              int64_t ldd, int64_t T, int64_t M, int64_t N, float alpha, int accumulate,
                              int precision, b200q_stream_t stream) {
+  if (precision == B200Q_BF16X3) precision = B200Q_TF32X3;   // BF16x3 is a Hessian-only mode; dense solves use TF32x3
   using namespace b200q;
   B200Q_REQUIRE(A && B && D && T >= 0 && M >= 0 && N >= 0, B200Q_ERR_INVALID_ARG, "bad argument");
   B200Q_REQUIRE(lda >= M && ldb >= N && ldd >= N, B200Q_ERR_INVALID_ARG, "leading dimension too small");

@@ -19,6 +19,7 @@
 // into hi = tf32(x) and lo = x - hi so that D += Ah*Bh + Ah*Bl + Al*Bh recovers fp32 accuracy.
 // Two 256-column accumulators (all 512 TMEM columns) double-buffer MMA against the epilogue.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -170,6 +171,52 @@ __device__ __forceinline__ void decode_unit(const HessianParams& p, int unit, in
   ib = 0; jb = 0;
 }
 
+// ===== epilogue (warps 4-7 of every tensor-core kernel below): TMEM -> registers -> alpha * acc
+// added into the upper triangle of H with 16-byte float reductions =====
+__device__ __forceinline__ void hessian_epilogue(const HessianParams& p, uint32_t tmem_base, uint64_t* tmem_full,
+                                                 uint64_t* tmem_empty, int n_units, int warp, int lane) {
+  const int q = warp & 3;   // TMEM lane quarter this warp may read
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    int ib, jb, sp;
+    decode_unit(p, unit, ib, jb, sp);
+    mbar_wait(&tmem_full[acc], acc_phase);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t i = (int64_t)ib * kTileM + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kTileN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + c0), r);
+      const int64_t j0 = (int64_t)jb * kTileN + c0;
+#ifdef B200Q_HESSIAN_PROBE
+      if (p.dbg_acc && unit == 0)
+        for (int c = 0; c < 32; ++c) p.dbg_acc[(q * 32 + lane) * kTileN + c0 + c] = __uint_as_float(r[c]);
+#endif
+      if (i < p.K && j0 < p.K && j0 + 31 >= i) {   // K % 32 == 0: a 32-column run is all in or all out
+        float* dst = p.H + i * p.K + j0;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float v0 = p.alpha * __uint_as_float(r[c]), v1 = p.alpha * __uint_as_float(r[c + 1]);
+          const float v2 = p.alpha * __uint_as_float(r[c + 2]), v3 = p.alpha * __uint_as_float(r[c + 3]);
+          if (j0 + c >= i) {            // whole quad on or above the diagonal: one 16-byte reduction
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v0), "f"(v1),
+                         "f"(v2), "f"(v3)
+                         : "memory");
+          } else if (j0 + c + 3 >= i) { // the quad straddles the diagonal
+            if (j0 + c + 1 >= i) atomicAdd(dst + c + 1, v1);
+            if (j0 + c + 2 >= i) atomicAdd(dst + c + 2, v2);
+            atomicAdd(dst + c + 3, v3);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&tmem_empty[acc]);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+}
+
 template <bool X3>
 __global__ void __launch_bounds__(X3 ? kThreads3 : kThreads1, 1)
 hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) {
@@ -288,47 +335,7 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===== epilogue: TMEM -> registers -> alpha * acc added into H and its mirror =====
-    const int q = warp & 3;   // TMEM lane quarter this warp may read
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      int ib, jb, sp;
-      decode_unit(p, unit, ib, jb, sp);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t i = (int64_t)ib * kTileM + q * 32 + lane;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kTileN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + c0), r);
-        const int64_t j0 = (int64_t)jb * kTileN + c0;
-#ifdef B200Q_HESSIAN_PROBE
-        if (p.dbg_acc && unit == 0)
-          for (int c = 0; c < 32; ++c) p.dbg_acc[(q * 32 + lane) * kTileN + c0 + c] = __uint_as_float(r[c]);
-#endif
-        if (i < p.K && j0 < p.K && j0 + 31 >= i) {   // K % 32 == 0: a 32-column run is all in or all out
-          float* dst = p.H + i * p.K + j0;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float v0 = p.alpha * __uint_as_float(r[c]), v1 = p.alpha * __uint_as_float(r[c + 1]);
-            const float v2 = p.alpha * __uint_as_float(r[c + 2]), v3 = p.alpha * __uint_as_float(r[c + 3]);
-            if (j0 + c >= i) {            // whole quad on or above the diagonal: one 16-byte reduction
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v0), "f"(v1),
-                           "f"(v2), "f"(v3)
-                           : "memory");
-            } else if (j0 + c + 3 >= i) { // the quad straddles the diagonal
-              if (j0 + c + 1 >= i) atomicAdd(dst + c + 1, v1);
-              if (j0 + c + 2 >= i) atomicAdd(dst + c + 2, v2);
-              atomicAdd(dst + c + 3, v3);
-            }
-          }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    hessian_epilogue(p, tmem_base, tmem_full, tmem_empty, n_units, warp, lane);
   } else if (X3 && warp >= 8) {
     // ===== converter (TF32x3): x -> hi = tf32(x) in place, lo = x - hi in the second buffer =====
     const int ct = threadIdx.x - 256;   // 0..127
@@ -361,6 +368,196 @@ hessian_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) 
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
+// =================================================================================================
+// BF16x3: X = b1 + b2 (+ r, |r| <= 2^-17 |x|) with b1 = bf16(x), b2 = bf16(x - b1), and
+// X^T X ~= b1^T b1 + b1^T b2 + b2^T b1 on kind::f16 (bf16 inputs, fp32 accumulate) at twice the
+// tf32 MMA rate.  The dropped terms are <= 3 * 2^-18 relative per product (measured on the
+// assembled H: 3e-6, below the 1e-5 of the truncating TMEM accumulation that every mode shares).
+// A pre-pass writes the two planes TRANSPOSED (channel-major, tokens contiguous), so that both MMA
+// operands are plain K-major SWIZZLE_128B tiles straight from TMA — no in-kernel splitter, no
+// shared-memory round trip: per 64-token stage 96 KB land and 72 KB are read by the tensor core
+// (TF32x3: 48 + 48 + 48 + 144 KB per 32 tokens).
+// =================================================================================================
+constexpr int kBfTT = 64;                                  // tokens per stage: 128 B of bf16 = the swizzle span
+constexpr int kBfABytes = kTileM * kBfTT * 2;              // 16 KB per plane
+constexpr int kBfBBytes = kTileN * kBfTT * 2;              // 32 KB per plane
+constexpr int kBfStageBytes = 2 * (kBfABytes + kBfBBytes); // 96 KB
+constexpr int kBfStages = 2;
+constexpr int kBfThreads = 256;
+
+// (tc tokens, K channels) fp32 row-major -> planes[2][K][tc_pad] bf16; tokens [tc, tc_pad) are zero
+__global__ void __launch_bounds__(256) hessian_split_bf16_kernel(const float* __restrict__ X, int64_t tc, int64_t K,
+                                                                 int64_t tc_pad, __nv_bfloat16* __restrict__ planes) {
+  __shared__ __nv_bfloat16 s1[64][72], s2[64][72];   // [channel][token], 144-byte rows
+  const int64_t t0 = (int64_t)blockIdx.x * 64, k0 = (int64_t)blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  {
+    const int cq = tid & 15, tr = tid >> 4;            // channel quad, token row (16 rows per pass)
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int tl = pass * 16 + tr;
+      const int64_t t = t0 + tl, k = k0 + cq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < tc && k < K) v = ldg_stream4(X + t * K + k);   // K % 4 == 0 on this route
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(xs[c]);
+        const __nv_bfloat16 b2 = __float2bfloat16_rn(xs[c] - __bfloat162float(b1));
+        s1[cq * 4 + c][tl] = b1;
+        s2[cq * 4 + c][tl] = b2;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int seg = tid & 7, ch = tid >> 3;            // 8 tokens (16 B) per store, 32 channels per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int c = pass * 32 + ch;
+      const int64_t k = k0 + c, t = t0 + seg * 8;
+      if (k < K && t < tc_pad) {
+        *reinterpret_cast<uint4*>(planes + k * tc_pad + t) = *reinterpret_cast<const uint4*>(&s1[c][seg * 8]);
+        *reinterpret_cast<uint4*>(planes + (K + k) * tc_pad + t) = *reinterpret_cast<const uint4*>(&s2[c][seg * 8]);
+      }
+    }
+  }
+}
+
+// SM100 shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes (64 bf16
+// tokens of one channel), 8-row swizzle atoms 1024 bytes apart (SBO); LBO is unused for swizzled
+// K-major layouts.  A K step of 16 elements advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp32 accumulate, A and B bf16, both K-major, M x N
+constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// tmap: planes as 3-D (tokens, channels, plane), box (64, 128, 1).  p.T = padded tokens of this call.
+__global__ void __launch_bounds__(kBfThreads, 1)
+hessian_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kBfStages * kBfStageBytes);
+  uint64_t* empty_bar = full_bar + kBfStages;
+  uint64_t* tmem_full = empty_bar + kBfStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = p.n_tiles * p.splits;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kBfStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: per stage A1, B1 (two boxes), A2, B2 (two boxes) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int ib, jb, sp;
+        decode_unit(p, unit, ib, jb, sp);
+        const int64_t t0 = (int64_t)sp * p.t_per_split;
+        const int64_t t1 = min(t0 + p.t_per_split, p.T);
+        for (int64_t t = t0; t < t1; t += kBfTT) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sb = smem + stage * kBfStageBytes;
+          mbar_expect_tx(&full_bar[stage], kBfStageBytes);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            unsigned char* base = sb + pl * (kBfABytes + kBfBBytes);
+            tma_load_3d(base, &tmap, &full_bar[stage], (int)t, ib * kTileM, pl);
+            tma_load_3d(base + kBfABytes, &tmap, &full_bar[stage], (int)t, jb * kTileN, pl);
+            tma_load_3d(base + kBfABytes + kBfABytes, &tmap, &full_bar[stage], (int)t, jb * kTileN + 128, pl);
+          }
+          if (++stage == kBfStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kTileN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int ib, jb, sp;
+        decode_unit(p, unit, ib, jb, sp);
+        const int64_t t0 = (int64_t)sp * p.t_per_split;
+        const int64_t t1 = min(t0 + p.t_per_split, p.T);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + (uint32_t)acc * kTileN;
+        uint32_t accumulate = 0;
+        for (int64_t t = t0; t < t1; t += kBfTT) {
+          mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a1 = smem_u32(smem + stage * kBfStageBytes), b1 = a1 + kBfABytes;
+          const uint32_t a2 = a1 + kBfABytes + kBfBBytes, b2 = a2 + kBfABytes;
+#pragma unroll
+          for (int k = 0; k < kBfTT / 16; ++k) {
+            const uint64_t da1 = umma_desc_k_sw128(a1 + k * 32), db1 = umma_desc_k_sw128(b1 + k * 32);
+            const uint64_t da2 = umma_desc_k_sw128(a2 + k * 32), db2 = umma_desc_k_sw128(b2 + k * 32);
+            umma_bf16(d, da1, db1, idesc, accumulate);
+            accumulate = 1;
+            umma_bf16(d, da1, db2, idesc, 1);
+            umma_bf16(d, da2, db1, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kBfStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    hessian_epilogue(p, tmem_base, tmem_full, tmem_empty, n_units, warp, lane);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -442,18 +639,30 @@ using namespace b200q;
 
 extern "C" {
 
+// BF16x3: tokens per pre-split chunk.  The two bf16 planes of a chunk (4 bytes per element in all)
+// are sized to stay in L2 between the split pass that writes them and the MMA kernel that reads
+// them, so HBM only sees X once.
+static int64_t bf16_chunk_tokens(int64_t T, int64_t K) {
+  int64_t tc = ((64ll << 20) / (4 * K)) / 1024 * 1024;
+  if (tc < 1024) tc = 1024;
+  if (tc > 16384) tc = 16384;
+  const int64_t t_pad = (T + kBfTT - 1) / kBfTT * kBfTT;
+  return tc < t_pad ? tc : t_pad;
+}
+
 size_t b200q_hessian_workspace_bytes(int64_t T, int64_t K, int precision) {
-  (void)T; (void)K; (void)precision;
-  return 256;   // nothing needed today; kept in the ABI so a split-K reduction buffer can be added
+  if (precision == B200Q_BF16X3 && T > 0 && K > 0 && K % 4 == 0)
+    return (size_t)bf16_chunk_tokens(T, K) * (size_t)K * 4 + 1024;
+  return 256;
 }
 
 int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, float beta, float* H,
                              int precision, void* workspace, size_t workspace_bytes,
                              b200q_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   cudaStream_t st = (cudaStream_t)stream;
   B200Q_REQUIRE(X && H && T > 0 && K > 0, B200Q_ERR_INVALID_ARG, "bad argument");
-  B200Q_REQUIRE(precision == B200Q_TF32 || precision == B200Q_TF32X3 || precision == B200Q_FP32_SIMT,
+  B200Q_REQUIRE(precision == B200Q_TF32 || precision == B200Q_TF32X3 || precision == B200Q_FP32_SIMT ||
+                    precision == B200Q_BF16X3,
                 B200Q_ERR_INVALID_ARG, "unknown precision %d", precision);
   B200Q_REQUIRE(T < (1ll << 31) && K < (1ll << 31), B200Q_ERR_UNSUPPORTED, "T and K must fit in int32");
   // H <- beta * H
@@ -497,6 +706,48 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
   p.n_jb = (int)ceil_div(K, kTileN);
   p.n_tiles = 0;
   for (int ib = 0; ib < p.n_ib; ++ib) p.n_tiles += p.n_jb - (ib * kTileM) / kTileN;
+
+  if (precision == B200Q_BF16X3) {
+    const int64_t tc_max = bf16_chunk_tokens(T, K);
+    const size_t need = (size_t)tc_max * (size_t)K * 4 + 1024;
+    B200Q_REQUIRE(workspace && workspace_bytes >= need, B200Q_ERR_WORKSPACE,
+                  "workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    __nv_bfloat16* planes = (__nv_bfloat16*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    const size_t smem = (size_t)kBfStages * kBfStageBytes + 1024 + 256;
+    B200Q_CUDA_OK(cudaFuncSetAttribute(hessian_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    for (int64_t c0 = 0; c0 < T; c0 += tc_max) {
+      const int64_t tc = T - c0 < tc_max ? T - c0 : tc_max;
+      const int64_t tc_pad = (tc + kBfTT - 1) / kBfTT * kBfTT;
+      dim3 sgrid((unsigned)(tc_pad / 64), (unsigned)ceil_div(K, 64));
+      hessian_split_bf16_kernel<<<sgrid, 256, 0, st>>>(X + c0 * K, tc, K, tc_pad, planes);
+      B200Q_LAUNCH_OK();
+      CUtensorMap bmap;
+      cuuint64_t bdims[3] = {(cuuint64_t)tc_pad, (cuuint64_t)K, 2};
+      cuuint64_t bstrides[2] = {(cuuint64_t)tc_pad * 2, (cuuint64_t)K * (cuuint64_t)tc_pad * 2};
+      cuuint32_t bbox[3] = {(cuuint32_t)kBfTT, 128, 1};
+      cuuint32_t bestr[3] = {1, 1, 1};
+      CUresult bcr = encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)planes, bdims, bstrides, bbox, bestr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      B200Q_REQUIRE(bcr == CUDA_SUCCESS, B200Q_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 planes) failed (%d)", (int)bcr);
+      // units of <= 1024 tokens (192 MMAs, the same accumulation-chain length as TF32x3's 512)
+      int64_t chunk_stages = 1024 / kBfTT;
+      const int64_t stages_total = tc_pad / kBfTT;
+      while (chunk_stages > 4 && p.n_tiles * ceil_div(stages_total, chunk_stages) < 2 * kNumSMs) chunk_stages /= 2;
+      HessianParams q = p;
+      q.T = tc_pad;
+      q.t_per_split = chunk_stages * kBfTT;
+      q.splits = (int)ceil_div(tc_pad, q.t_per_split);
+      const int n_units = q.n_tiles * q.splits;
+      hessian_bf16x3_kernel<<<n_units < kNumSMs ? n_units : kNumSMs, kBfThreads, smem, st>>>(bmap, q);
+      B200Q_LAUNCH_OK();
+    }
+    dim3 mgrid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(K, 32));
+    mirror_upper_kernel<<<mgrid, dim3(32, 8), 0, st>>>(H, K);
+    B200Q_LAUNCH_OK();
+    return B200Q_OK;
+  }
   // Token chunk per unit.  The tensor core adds into the fp32 TMEM accumulator with truncation, so a
   // chain of n MMAs carries a bias of about n * 2^-25 relative (measured on B200); every unit ends
   // with a round-to-nearest reduction into H, so the chunk length bounds the bias: 512 tokens

@@ -260,6 +260,7 @@ size_t b200q_hinv_workspace_bytes(int64_t K) {
 int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int actorder, float* U,
                               int32_t* perm, unsigned char* dead, int32_t* status, int precision,
                               void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  if (precision == B200Q_BF16X3) precision = B200Q_TF32X3;   // BF16x3 is a Hessian-only mode; dense solves use TF32x3
   cudaStream_t st = (cudaStream_t)stream;
   B200Q_REQUIRE(H && U && perm && dead && status && K > 0, B200Q_ERR_INVALID_ARG, "bad argument");
   B200Q_REQUIRE(K < (1ll << 31), B200Q_ERR_UNSUPPORTED, "K must fit in int32");

@@ -10,7 +10,7 @@ shapes = [(32768, 4096), (16384, 14336), (65536, 1152)] if len(sys.argv) < 2 els
 for (t, k) in shapes:
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     x = torch.randn((t, k), device="cuda", generator=g)
-    for prec in ("tf32", "tf32x3"):
+    for prec in ("tf32", "tf32x3", "bf16x3"):
         h = torch.zeros((k, k), device="cuda")
         for _ in range(2):
             hessian_accumulate(x, h, 1.0 / t, 1.0, precision=prec)
@@ -26,7 +26,8 @@ for (t, k) in shapes:
     if t * k <= 2**28:
         want = (x.double().T @ x.double()) / t
         h = torch.zeros((k, k), device="cuda")
-        hessian_accumulate(x, h, 1.0 / t, 0.0, precision="tf32x3")
-        print("   tf32x3 max rel err", ((h.double() - want).abs().max() / want.abs().max()).item())
+        for prec in ("tf32x3", "bf16x3"):
+            hessian_accumulate(x, h, 1.0 / t, 0.0, precision=prec)
+            print("  ", prec, "max rel err", ((h.double() - want).abs().max() / want.abs().max()).item())
     del x
 print("ok")
