@@ -56,7 +56,7 @@ def parse():
     p.add_argument("--no-gptq", action="store_true")
     p.add_argument("--gptq-layers", type=int, default=4,
                    help="Llama-3-8B-shaped layers in the GPTQ sample (the model has 32)")
-    p.add_argument("--gptq-precision", default="tf32x3", choices=["tf32", "tf32x3"])
+    p.add_argument("--gptq-precision", default="bf16x3", choices=["tf32", "tf32x3", "bf16x3"])
     return p.parse_args()
 
 
@@ -296,7 +296,7 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
     def executed(k):   # the kernel only computes the 128x256 tiles that touch the upper triangle
         n_ib, n_jb = -(-k // 128), -(-k // 256)
         tiles = sum(max(n_jb - (ib * 128) // 256, 0) for ib in range(n_ib))
-        return 2.0 * tokens * tiles * 128 * 256 * (3 if args.gptq_precision == "tf32x3" else 1)
+        return 2.0 * tokens * tiles * 128 * 256 * (1 if args.gptq_precision == "tf32" else 3)
 
     mma_flops = sum(executed(GPTQ_GROUPS[gi][1]) for _, gi in units)
     peaks = {}
@@ -307,6 +307,8 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
         pass
     bf16 = float(peaks.get("bf16_tflops_sustained", 1393.9))
     tf = mma_flops / world / (hess_ms * 1e-3) / 1e12       # per GPU: every rank contracts tokens/world
+    is_bf16 = args.gptq_precision == "bf16x3"
+    mma_peak = bf16 if is_bf16 else bf16 / 2
     out = {
         "workload": f"GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
                     f"{model}-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
@@ -316,11 +318,14 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
         "extrapolation": f"x{model_layers / layers:g}: the {model_layers} layers are identical in shape",
         "hessian_s": hess_ms * 1e-3, "hessian_reduce_s": red_ms * 1e-3, "solve_s": solve_ms * 1e-3,
         "hessian_tflops_algorithmic": flops / (hess_ms * 1e-3) / 1e12,
-        "roofline": {"bound": "tensor", "kernel": "hessian_kernel", "achieved": tf, "unit": "TFLOP/s",
-                     "peak": bf16 / 2, "frac": tf / (bf16 / 2),
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the "
-                                    "bf16 rate); achieved = tf32 MMA flops actually issued per GPU (upper-triangle "
-                                    "tiles only, x3 products in 3xTF32 mode) / Hessian time",
+        "roofline": {"bound": "tensor", "kernel": "hessian_bf16x3_kernel" if is_bf16 else "hessian_kernel",
+                     "achieved": tf, "unit": "TFLOP/s", "peak": mma_peak, "frac": tf / mma_peak,
+                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kind::f16, bf16 inputs); achieved = bf16 "
+                                     "MMA flops actually issued per GPU (upper-triangle tiles only, the 3 products of "
+                                     "the BF16x3 split) / Hessian time, split pre-pass included") if is_bf16 else
+                                    ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the "
+                                     "bf16 rate); achieved = tf32 MMA flops actually issued per GPU (upper-triangle "
+                                     "tiles only, x3 products in 3xTF32 mode) / Hessian time"),
                      "flops": flops},
     }
     del xs, ws, hs

@@ -26,7 +26,7 @@ from onnx_quantize_b200.hessian import hessian_accumulate
 class AwqStatistics:
     """Streaming calibration statistics of one layer input: ``G = Σ XᵀX``, ``Σ|x|``, token count."""
 
-    def __init__(self, k: int, precision: str = "tf32x3", device=None):
+    def __init__(self, k: int, precision: str = "bf16x3", device=None):
         self.device = device or dev.require_cuda()
         self.gram = torch.zeros((k, k), dtype=torch.float32, device=self.device)
         self.abs_sum = torch.zeros((k,), dtype=torch.float32, device=self.device)
@@ -90,7 +90,7 @@ def weight_scale(w: torch.Tensor, strategy, group_size=-1) -> torch.Tensor:
 
 
 def awq_search(weights, stats: AwqStatistics, quant_type, strategy, group_size=-1, is_symmetric=False,
-               reduce_range=False, clip_search=False, n_grid: int = 20, precision: str = "tf32x3") -> AwqResult:
+               reduce_range=False, clip_search=False, n_grid: int = 20, precision: str = "bf16x3") -> AwqResult:
     """The scale grid (and optionally the clip grid) of the reference's AWQ pass for one weight."""
     lib = _lib.load()
     w = dev.to_device_f32(weights)

@@ -43,7 +43,7 @@ class GPTQConfig(AlgorithmConfig):
     percdamp: float = 0.01
     actorder: bool = False
     mode: Literal["reference", "propagate"] = "reference"
-    precision: Literal["tf32", "tf32x3", "fp32"] = "tf32x3"
+    precision: Literal["tf32", "tf32x3", "bf16x3", "fp32"] = "bf16x3"
 
     def quantize_weights(self, w: "ir.Value", qconfig: "QConfig", out: "ir.Value | None" = None
                          ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -73,7 +73,7 @@ _FALLBACK_WARNING = (
 )   # the reference's message (gptq.py:144-149)
 
 
-def _accumulate_hessian(inp, H, num_samples, precision="tf32x3"):
+def _accumulate_hessian(inp, H, num_samples, precision="bf16x3"):
     """``H ← H·n/(n+b) + (2/(n+b))·XᵀX`` with ``b = inp.shape[0]`` samples (gptq.py:246-260).
 
     ``H`` may be a NumPy array (staged to the device and back, returned as NumPy like the
@@ -94,7 +94,7 @@ def _accumulate_hessian(inp, H, num_samples, precision="tf32x3"):
 
 def _gptq(W, H, quant_type, strategy, group_size, is_symmetric, reduce_range, clip_ratio,
           block_size, percdamp, actorder, mse, scale_dtype, zp_dtype, mode="reference",
-          precision="tf32x3"):
+          precision="bf16x3"):
     """GPTQ of one (K,N) weight given its (K,K) Hessian → ``(codes, scale, zero_point)``.
 
     Shapes and dtypes are the reference's (gptq.py:76-243).  ``W`` / ``H`` may be NumPy arrays or
@@ -123,7 +123,7 @@ def _gptq_quantize(weights, inputs, quant_type=QuantType.QInt8,
                    strategy=QuantizationStrategy.CHANNEL, group_size=32, is_symmetric=False,
                    reduce_range=False, clip_ratio=1.0, block_size=128, percdamp=0.01,
                    actorder=False, mse=False, scale_dtype=np.float32, zp_dtype=np.int8,
-                   mode="reference", precision="tf32x3"):
+                   mode="reference", precision="bf16x3"):
     """Hessian from ``inputs`` (num_samples, ..., in_features), then :func:`_gptq`
     (gptq.py:263-324).  The Hessian never leaves the device."""
     import torch

@@ -8,7 +8,7 @@ from onnx_quantize_b200 import _lib
 
 
 def hessian_accumulate(x: torch.Tensor, h: torch.Tensor, alpha: float, beta: float,
-                       precision: str = "tf32x3") -> torch.Tensor:
+                       precision: str = "bf16x3") -> torch.Tensor:
     """H <- beta*H + alpha * XᵀX in place; ``x`` is (..., K) float32 CUDA, ``h`` (K,K) float32."""
     lib = _lib.load()
     if not (x.is_cuda and x.dtype == torch.float32 and h.is_cuda and h.dtype == torch.float32):
@@ -33,7 +33,7 @@ class HessianAccumulator:
     folded as they arrive, activations are never kept.  ``num_samples`` counts *samples* (the
     leading dimension of each batch), exactly as the reference does."""
 
-    def __init__(self, k: int, precision: str = "tf32x3", device=None):
+    def __init__(self, k: int, precision: str = "bf16x3", device=None):
         self.device = device or dev.require_cuda()
         self.h = torch.zeros((k, k), dtype=torch.float32, device=self.device)
         self.num_samples = 0

@@ -241,6 +241,41 @@ def test_propagate_quality_and_parity(cuda, precision, qt, gs, sym, actorder):
         assert e_got < e_ref                            # real GPTQ beats the reference as written
 
 
+@pytest.mark.parametrize("hprec", ["bf16x3", "tf32x3"])
+def test_device_hessian_feeds_propagate_within_tolerance(cuda, hprec):
+    """The whole device chain — Hessian on the tensor cores in the given split mode, factor, GPTQ
+    loop — against the oracle fed with NumPy's own float32 Hessian: <= 0.1 % of the int4 codes
+    differ (by 1), layer-output relative MSE within 1 % (BASELINE.json north_star)."""
+    from onnx_quantize_b200.hessian import HessianAccumulator
+    rng = np.random.default_rng(11)
+    k, n = 512, 384
+    x = (rng.standard_normal((16, 128, k)) * rng.uniform(0.3, 3.0, k)).astype(np.float32)
+    x[..., 1:] += 0.5 * x[..., :-1]                       # correlated channels: the factor matters
+    w = (rng.standard_normal((k, n)) * 0.05).astype(np.float32)
+    acc = HessianAccumulator(k, precision=hprec)
+    for b in np.array_split(x, 4):
+        acc.add(b)
+    h_np = np.zeros((k, k), np.float32)
+    ns = 0
+    for b in np.array_split(x, 4):
+        h_np, ns = O.accumulate_hessian(b, h_np, ns)
+    f = G.hinv_cholesky_upper(acc.h, 0.01, False, hprec)
+    codes, s, z, deq = G.gptq_quantize(torch.from_numpy(w).to(cuda), f, QT["int4"], "group", 128, True, False, 1.0,
+                                       False, 128, "propagate", hprec, return_deq=True)
+    want = O.gptq(w, h_np, "int4", "group", 128, True, False, 1.0, 128, 0.01, False, False, O.np_dtype("int4"),
+                  "propagate", return_aux=True)
+    got_codes = codes.cpu().numpy().view(np.int8)
+    got_codes = np.where(got_codes > 7, got_codes - 16, got_codes)
+    diff = np.abs(got_codes.astype(np.int32) - as_i8(want[0], "int4").astype(np.int32))
+    # a flipped code changes the error that is propagated down its column; with correlated channels
+    # (|U[i,j]/U[i,i]| > 1) the cascade can move a later element by two steps — seen for 1 element in
+    # 196 608 with either split mode, never with the fp32 Hessian
+    assert (diff != 0).mean() <= 1e-3 and diff.max() <= 2 and (diff > 1).mean() <= 2e-5, \
+        (diff.max(), (diff != 0).mean(), (diff > 1).mean())
+    e, e_want = O.layer_output_rel_mse(x, w, deq.cpu().numpy()), O.layer_output_rel_mse(x, w, want[3]["deq"])
+    assert abs(e - e_want) <= 0.01 * e_want, (e, e_want)
+
+
 def test_streaming_hessian_then_gptq_on_device(cuda, rng):
     """The device-resident flow the multi-GPU driver uses: H never leaves the GPU."""
     k, n = 256, 64
