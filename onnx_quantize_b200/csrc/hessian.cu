@@ -393,45 +393,80 @@ constexpr int kBfABytes = kTileM * kBfTT * 2;              // 16 KB per plane
 constexpr int kBfBBytes = kTileN * kBfTT * 2;              // 32 KB per plane
 constexpr int kBfStageBytes = 2 * (kBfABytes + kBfBBytes); // 96 KB
 constexpr int kBfStages = 2;
-constexpr int kBfThreads = 256;
+constexpr int kBfThreads = 512;                            // warps 0-7 as in the tf32 kernels, warps 8-15 split the next chunk
 
-// (tc tokens, K channels) fp32 row-major -> planes[2][K][tc_pad] bf16; tokens [tc, tc_pad) are zero
-__global__ void __launch_bounds__(256) hessian_split_bf16_kernel(const float* __restrict__ X, int64_t tc, int64_t K,
-                                                                 int64_t tc_pad, __nv_bfloat16* __restrict__ planes) {
-  __shared__ __nv_bfloat16 s1[64][72], s2[64][72];   // [channel][token], 144-byte rows
-  const int64_t t0 = (int64_t)blockIdx.x * 64, k0 = (int64_t)blockIdx.y * 64;
-  const int tid = threadIdx.x;
-  {
-    const int cq = tid & 15, tr = tid >> 4;            // channel quad, token row (16 rows per pass)
+// (tc tokens, K channels) fp32 row-major -> planes[2][K][tc_pad] bf16; tokens [tc, tc_pad) are zero.
+// 64 x 64 tiles are transposed through shared memory as 32-bit words holding the bf16 values of
+// two consecutive tokens; the odd row pitch (33 words) makes both the channel-strided stores of
+// the load phase and the token-strided loads of the store phase bank-conflict free (the first
+// version stored 16-bit values at a 144-byte pitch: 8-way conflicts, 3.2 TB/s; see profiles/).
+// Executed by 256 threads (`tid` 0..255, named barrier 1) that walk tiles worker, worker +
+// n_workers, ...; the loads of the next tile are in flight while the current one is written out.
+// Two users: the stand-alone kernel below (first chunk of a call) and warps 8-15 of the MMA kernel,
+// which convert chunk c+1 into the other plane buffer while the tensor core works on chunk c.
+struct SplitJob {
+  const float* X;            // first token of the chunk; nullptr = nothing to do
+  int64_t tc, tc_pad, K;
+  __nv_bfloat16* planes;
+};
+constexpr int kSplitSmemBytes = 2 * 64 * 33 * 4;
+
+__device__ __forceinline__ void split_load(const SplitJob& j, int64_t tile, int64_t n_ky, int tid, float4 (&v)[2][2]) {
+  const int64_t t0 = (tile / n_ky) * 64, k0 = (tile % n_ky) * 64;   // channel blocks fastest: full rows of X per sweep
+  const int cq = tid & 15, tp = tid >> 4;
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int tl = pass * 16 + tr;
-      const int64_t t = t0 + tl, k = k0 + cq * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < tc && k < K) v = ldg_stream4(X + t * K + k);   // K % 4 == 0 on this route
-      const float xs[4] = {v.x, v.y, v.z, v.w};
+  for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const __nv_bfloat16 b1 = __float2bfloat16_rn(xs[c]);
-        const __nv_bfloat16 b2 = __float2bfloat16_rn(xs[c] - __bfloat162float(b1));
-        s1[cq * 4 + c][tl] = b1;
-        s2[cq * 4 + c][tl] = b2;
-      }
+    for (int h = 0; h < 2; ++h) {
+      const int64_t t = t0 + 2 * (pass * 16 + tp) + h, k = k0 + cq * 4;
+      v[pass][h] = (t < j.tc && k < j.K) ? ldg_stream4(j.X + t * j.K + k) : make_float4(0.f, 0.f, 0.f, 0.f);   // K % 4 == 0
     }
   }
-  __syncthreads();
-  {
-    const int seg = tid & 7, ch = tid >> 3;            // 8 tokens (16 B) per store, 32 channels per pass
+}
+
+__device__ __forceinline__ void split_tiles(const SplitJob& j, uint32_t* smem_words, int worker, int n_workers, int tid) {
+  if (j.X == nullptr) return;
+  uint32_t (*s1)[33] = reinterpret_cast<uint32_t (*)[33]>(smem_words);
+  uint32_t (*s2)[33] = reinterpret_cast<uint32_t (*)[33]>(smem_words + 64 * 33);
+  const int64_t n_ky = (j.K + 63) / 64, total = (j.tc_pad / 64) * n_ky;
+  const int cq = tid & 15, tp = tid >> 4, lane = tid & 31, w = tid >> 5;
+  uint32_t* p1 = reinterpret_cast<uint32_t*>(j.planes);
+  float4 v[2][2];
+  int64_t tile = worker;
+  if (tile < total) split_load(j, tile, n_ky, tid, v);
+  for (; tile < total; tile += n_workers) {
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
-      const int c = pass * 32 + ch;
-      const int64_t k = k0 + c, t = t0 + seg * 8;
-      if (k < K && t < tc_pad) {
-        *reinterpret_cast<uint4*>(planes + k * tc_pad + t) = *reinterpret_cast<const uint4*>(&s1[c][seg * 8]);
-        *reinterpret_cast<uint4*>(planes + (K + k) * tc_pad + t) = *reinterpret_cast<const uint4*>(&s2[c][seg * 8]);
+      const float x0[4] = {v[pass][0].x, v[pass][0].y, v[pass][0].z, v[pass][0].w};
+      const float x1[4] = {v[pass][1].x, v[pass][1].y, v[pass][1].z, v[pass][1].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const __nv_bfloat16 a0 = __float2bfloat16_rn(x0[c]), a1 = __float2bfloat16_rn(x1[c]);
+        const __nv_bfloat16 r0 = __float2bfloat16_rn(x0[c] - __bfloat162float(a0));
+        const __nv_bfloat16 r1 = __float2bfloat16_rn(x1[c] - __bfloat162float(a1));
+        s1[cq * 4 + c][pass * 16 + tp] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
+        s2[cq * 4 + c][pass * 16 + tp] = (uint32_t)__bfloat16_as_ushort(r0) | ((uint32_t)__bfloat16_as_ushort(r1) << 16);
       }
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tile + n_workers < total) split_load(j, tile + n_workers, n_ky, tid, v);   // in flight during the write-out
+    const int64_t t = (tile / n_ky) * 64 + 2 * lane, k0 = (tile % n_ky) * 64;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int c = w * 8 + r;
+      const int64_t k = k0 + c;
+      if (k < j.K) {
+        p1[(k * j.tc_pad + t) >> 1] = s1[c][lane];
+        p1[((j.K + k) * j.tc_pad + t) >> 1] = s2[c][lane];
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
+}
+
+__global__ void __launch_bounds__(256) hessian_split_bf16_kernel(const SplitJob j) {
+  __shared__ uint32_t words[kSplitSmemBytes / 4];
+  split_tiles(j, words, blockIdx.x, gridDim.x, threadIdx.x);
 }
 
 // SM100 shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes (64 bf16
@@ -462,9 +497,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-// tmap: planes as 3-D (tokens, channels, plane), box (64, 128, 1).  p.T = padded tokens of this call.
+// tmap: planes as 3-D (tokens, channels, plane), box (64, 128, 1).  p.T = padded tokens of this chunk.
+// `next` = the following chunk, converted into the other plane buffer by warps 8-15 meanwhile.
 __global__ void __launch_bounds__(kBfThreads, 1)
-hessian_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p) {
+hessian_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p, const SplitJob next) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + kBfStages * kBfStageBytes);
@@ -472,6 +508,7 @@ hessian_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap, const HessianPar
   uint64_t* tmem_full = empty_bar + kBfStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+  uint32_t* split_words = (uint32_t*)(smem + kBfStages * kBfStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles * p.splits;
@@ -558,6 +595,8 @@ hessian_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap, const HessianPar
     }
   } else if (warp >= 4 && warp < 8) {
     hessian_epilogue(p, tmem_base, tmem_full, tmem_empty, n_units, warp, lane);
+  } else if (warp >= 8) {
+    split_tiles(next, split_words, blockIdx.x, gridDim.x, threadIdx.x - 256);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -639,20 +678,25 @@ using namespace b200q;
 
 extern "C" {
 
-// BF16x3: tokens per pre-split chunk.  The two bf16 planes of a chunk (4 bytes per element in all)
-// are sized to stay in L2 between the split pass that writes them and the MMA kernel that reads
-// them, so HBM only sees X once.
+// BF16x3: tokens per pre-split chunk.  Two plane buffers (4 bytes per element each) let the split
+// pass of chunk c+1 run in the shadow of the MMA kernel of chunk c; long chunks keep the number of
+// partial waves of MMA units small (measured: tools/prof_hessian_bf16.py).
 static int64_t bf16_chunk_tokens(int64_t T, int64_t K) {
-  int64_t tc = ((64ll << 20) / (4 * K)) / 1024 * 1024;
+  int64_t tc = ((256ll << 20) / (4 * K)) / 1024 * 1024;
   if (tc < 1024) tc = 1024;
-  if (tc > 16384) tc = 16384;
+  if (tc > 32768) tc = 32768;
+  if (const char* e = getenv("B200Q_HESSIAN_BF16_CHUNK")) {   // experiment knob (tokens per pre-split chunk)
+    const long v = atol(e);
+    if (v >= 64) tc = v / 64 * 64;
+  }
   const int64_t t_pad = (T + kBfTT - 1) / kBfTT * kBfTT;
   return tc < t_pad ? tc : t_pad;
 }
+static size_t bf16_plane_bytes(int64_t tc, int64_t K) { return align_up((size_t)tc * (size_t)K * 4, 1024); }
 
 size_t b200q_hessian_workspace_bytes(int64_t T, int64_t K, int precision) {
   if (precision == B200Q_BF16X3 && T > 0 && K > 0 && K % 4 == 0)
-    return (size_t)bf16_chunk_tokens(T, K) * (size_t)K * 4 + 1024;
+    return 2 * bf16_plane_bytes(bf16_chunk_tokens(T, K), K) + 1024;
   return 256;
 }
 
@@ -709,30 +753,52 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
 
   if (precision == B200Q_BF16X3) {
     const int64_t tc_max = bf16_chunk_tokens(T, K);
-    const size_t need = (size_t)tc_max * (size_t)K * 4 + 1024;
+    const size_t need = 2 * bf16_plane_bytes(tc_max, K) + 1024;
     B200Q_REQUIRE(workspace && workspace_bytes >= need, B200Q_ERR_WORKSPACE,
                   "workspace of %zu bytes needed, %zu given", need, workspace_bytes);
-    __nv_bfloat16* planes = (__nv_bfloat16*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-    const size_t smem = (size_t)kBfStages * kBfStageBytes + 1024 + 256;
+    unsigned char* plane_base = (unsigned char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    const size_t smem = (size_t)kBfStages * kBfStageBytes + 1024 + 256 + kSplitSmemBytes;
     B200Q_CUDA_OK(cudaFuncSetAttribute(hessian_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    for (int64_t c0 = 0; c0 < T; c0 += tc_max) {
-      const int64_t tc = T - c0 < tc_max ? T - c0 : tc_max;
-      const int64_t tc_pad = (tc + kBfTT - 1) / kBfTT * kBfTT;
-      dim3 sgrid((unsigned)(tc_pad / 64), (unsigned)ceil_div(K, 64));
-      hessian_split_bf16_kernel<<<sgrid, 256, 0, st>>>(X + c0 * K, tc, K, tc_pad, planes);
+    auto job = [&](int64_t c0, int buf) {
+      SplitJob j;
+      j.X = nullptr; j.tc = 0; j.tc_pad = 0; j.K = K; j.planes = nullptr;
+      if (c0 < T) {
+        j.X = X + c0 * K;
+        j.tc = T - c0 < tc_max ? T - c0 : tc_max;
+        j.tc_pad = (j.tc + kBfTT - 1) / kBfTT * kBfTT;
+        j.planes = (__nv_bfloat16*)(plane_base + (size_t)buf * bf16_plane_bytes(tc_max, K));
+      }
+      return j;
+    };
+    {   // chunk 0: stand-alone split pass (every later chunk is converted inside the MMA kernel before it)
+      const SplitJob j0 = job(0, 0);
+      const int64_t tiles = (j0.tc_pad / 64) * ceil_div(K, 64);
+      hessian_split_bf16_kernel<<<(unsigned)(tiles < kNumSMs * 8 ? tiles : kNumSMs * 8), 256, 0, st>>>(j0);
       B200Q_LAUNCH_OK();
+    }
+    int buf = 0;
+    for (int64_t c0 = 0; c0 < T; c0 += tc_max, buf ^= 1) {
+      const SplitJob cur = job(c0, buf), next = job(c0 + tc_max, buf ^ 1);
+      const int64_t tc_pad = cur.tc_pad;
       CUtensorMap bmap;
       cuuint64_t bdims[3] = {(cuuint64_t)tc_pad, (cuuint64_t)K, 2};
       cuuint64_t bstrides[2] = {(cuuint64_t)tc_pad * 2, (cuuint64_t)K * (cuuint64_t)tc_pad * 2};
       cuuint32_t bbox[3] = {(cuuint32_t)kBfTT, 128, 1};
       cuuint32_t bestr[3] = {1, 1, 1};
-      CUresult bcr = encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)planes, bdims, bstrides, bbox, bestr,
+      CUresult bcr = encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)cur.planes, bdims, bstrides, bbox, bestr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       B200Q_REQUIRE(bcr == CUDA_SUCCESS, B200Q_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 planes) failed (%d)", (int)bcr);
-      // units of <= 1024 tokens (192 MMAs, the same accumulation-chain length as TF32x3's 512)
-      int64_t chunk_stages = 1024 / kBfTT;
+      // Tokens per unit = length of the truncating TMEM accumulation chain before a round-to-nearest
+      // reduction into H.  Measured (tools/prof_hessian_unit.py, max relative error vs float64):
+      // 512 -> 5e-6, 1024 -> 7e-6, 2048 -> 1.25e-5, 4096 -> 2.2e-5.  Every unit costs a 128 KB
+      // read-modify-write of H, which for K >= 2048 (H far larger than L2) is worth halving: +5 %.
+      int64_t chunk_stages = (K >= 2048 ? 2048 : 1024) / kBfTT;
+      if (const char* e = getenv("B200Q_HESSIAN_BF16_UNIT")) {   // experiment knob (tokens per MMA unit)
+        const long v = atol(e);
+        if (v >= kBfTT) chunk_stages = v / kBfTT;
+      }
       const int64_t stages_total = tc_pad / kBfTT;
       while (chunk_stages > 4 && p.n_tiles * ceil_div(stages_total, chunk_stages) < 2 * kNumSMs) chunk_stages /= 2;
       HessianParams q = p;
@@ -740,7 +806,9 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
       q.t_per_split = chunk_stages * kBfTT;
       q.splits = (int)ceil_div(tc_pad, q.t_per_split);
       const int n_units = q.n_tiles * q.splits;
-      hessian_bf16x3_kernel<<<n_units < kNumSMs ? n_units : kNumSMs, kBfThreads, smem, st>>>(bmap, q);
+      // with a chunk to convert every SM gets a CTA even when there are fewer MMA units than SMs
+      const int grid = (next.X != nullptr || n_units >= kNumSMs) ? kNumSMs : n_units;
+      hessian_bf16x3_kernel<<<grid, kBfThreads, smem, st>>>(bmap, q, next);
       B200Q_LAUNCH_OK();
     }
     dim3 mgrid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(K, 32));
