@@ -397,9 +397,10 @@ constexpr int kBfThreads = 512;                            // warps 0-7 as in th
 
 // (tc tokens, K channels) fp32 row-major -> planes[2][K][tc_pad] bf16; tokens [tc, tc_pad) are zero.
 // 64 x 64 tiles are transposed through shared memory as 32-bit words holding the bf16 values of
-// two consecutive tokens; the odd row pitch (33 words) makes both the channel-strided stores of
-// the load phase and the token-strided loads of the store phase bank-conflict free (the first
-// version stored 16-bit values at a 144-byte pitch: 8-way conflicts, 3.2 TB/s; see profiles/).
+// two consecutive tokens, the column index XOR-swizzled by the channel quad so that both the
+// channel-strided stores of the load phase and the token-strided loads of the store phase are
+// bank-conflict free (first version: 16-bit stores at a 144-byte pitch, 8-way conflicts, 3.2 TB/s;
+// second: pitch 33, still 2-way because channel quads alias every 8 — ncu in profiles/).
 // Executed by 256 threads (`tid` 0..255, named barrier 1) that walk tiles worker, worker +
 // n_workers, ...; the loads of the next tile are in flight while the current one is written out.
 // Two users: the stand-alone kernel below (first chunk of a call) and warps 8-15 of the MMA kernel,
@@ -409,7 +410,7 @@ struct SplitJob {
   int64_t tc, tc_pad, K;
   __nv_bfloat16* planes;
 };
-constexpr int kSplitSmemBytes = 2 * 64 * 33 * 4;
+constexpr int kSplitSmemBytes = 2 * 64 * 32 * 4;
 
 __device__ __forceinline__ void split_load(const SplitJob& j, int64_t tile, int64_t n_ky, int tid, float4 (&v)[2][2]) {
   const int64_t t0 = (tile / n_ky) * 64, k0 = (tile % n_ky) * 64;   // channel blocks fastest: full rows of X per sweep
@@ -426,8 +427,11 @@ __device__ __forceinline__ void split_load(const SplitJob& j, int64_t tile, int6
 
 __device__ __forceinline__ void split_tiles(const SplitJob& j, uint32_t* smem_words, int worker, int n_workers, int tid) {
   if (j.X == nullptr) return;
-  uint32_t (*s1)[33] = reinterpret_cast<uint32_t (*)[33]>(smem_words);
-  uint32_t (*s2)[33] = reinterpret_cast<uint32_t (*)[33]>(smem_words + 64 * 33);
+  // [channel][token pair] words, pitch 32, the column index XOR-ed with 2 * (channel / 4): the 32
+  // lanes of a store (16 channel quads x 2 token pairs) and of a load (32 token pairs of one
+  // channel) both hit 32 different banks
+  uint32_t* s1 = smem_words;
+  uint32_t* s2 = smem_words + 64 * 32;
   const int64_t n_ky = (j.K + 63) / 64, total = (j.tc_pad / 64) * n_ky;
   const int cq = tid & 15, tp = tid >> 4, lane = tid & 31, w = tid >> 5;
   uint32_t* p1 = reinterpret_cast<uint32_t*>(j.planes);
@@ -439,13 +443,16 @@ __device__ __forceinline__ void split_tiles(const SplitJob& j, uint32_t* smem_wo
     for (int pass = 0; pass < 2; ++pass) {
       const float x0[4] = {v[pass][0].x, v[pass][0].y, v[pass][0].z, v[pass][0].w};
       const float x1[4] = {v[pass][1].x, v[pass][1].y, v[pass][1].z, v[pass][1].w};
+      const int col = (pass * 16 + tp) ^ (2 * cq);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const __nv_bfloat16 a0 = __float2bfloat16_rn(x0[c]), a1 = __float2bfloat16_rn(x1[c]);
-        const __nv_bfloat16 r0 = __float2bfloat16_rn(x0[c] - __bfloat162float(a0));
-        const __nv_bfloat16 r1 = __float2bfloat16_rn(x1[c] - __bfloat162float(a1));
-        s1[cq * 4 + c][pass * 16 + tp] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
-        s2[cq * 4 + c][pass * 16 + tp] = (uint32_t)__bfloat16_as_ushort(r0) | ((uint32_t)__bfloat16_as_ushort(r1) << 16);
+        // one packed conversion per pair (F2FP on the ALU pipe; the scalar cvt is an XU instruction)
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(x0[c], x1[c]);
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hi);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x0[c] - __uint_as_float(hw << 16),
+                                                        x1[c] - __uint_as_float(hw & 0xFFFF0000u));
+        s1[(cq * 4 + c) * 32 + col] = hw;
+        s2[(cq * 4 + c) * 32 + col] = *reinterpret_cast<const uint32_t*>(&lo);
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -455,9 +462,10 @@ __device__ __forceinline__ void split_tiles(const SplitJob& j, uint32_t* smem_wo
     for (int r = 0; r < 8; ++r) {
       const int c = w * 8 + r;
       const int64_t k = k0 + c;
+      const int col = lane ^ (2 * (c >> 2));
       if (k < j.K) {
-        p1[(k * j.tc_pad + t) >> 1] = s1[c][lane];
-        p1[((j.K + k) * j.tc_pad + t) >> 1] = s2[c][lane];
+        p1[(k * j.tc_pad + t) >> 1] = s1[c * 32 + col];
+        p1[((j.K + k) * j.tc_pad + t) >> 1] = s2[c * 32 + col];
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
