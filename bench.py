@@ -57,6 +57,8 @@ def parse():
     p.add_argument("--gptq-layers", type=int, default=4,
                    help="Llama-3-8B-shaped layers in the GPTQ sample (the model has 32)")
     p.add_argument("--gptq-precision", default="bf16x3", choices=["tf32", "tf32x3", "bf16x3"])
+    p.add_argument("--gptq-streams", type=int, default=8,
+                   help="CUDA streams the independent GPTQ solves of a rank are spread over")
     return p.parse_args()
 
 
@@ -227,6 +229,7 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
     from onnx_quantize_b200.core._dtypes import QuantType
     from onnx_quantize_b200.hessian import hessian_accumulate
     from onnx_quantize_b200.parallel.shard import assign_units
+    from onnx_quantize_b200.parallel.streams import StreamPool
 
     layers = layers or args.gptq_layers
     tokens = GPTQ_SAMPLES * GPTQ_SEQ
@@ -249,6 +252,7 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
             owner[units[i]] = r
     alpha = 2.0 / GPTQ_SAMPLES
     hs = {}
+    pool = StreamPool(args.gptq_streams, device)
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -268,13 +272,15 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
             for u in units:
                 dist.reduce(hs[u], dst=owner[u], op=dist.ReduceOp.SUM)
         e2 = ev()
-        for u in units:                                    # G2-G4 on the owner
-            if owner[u] != rank:
-                continue
-            f = G.hinv_cholesky_upper(hs[u], 0.01, False, args.gptq_precision)
-            for shp in GPTQ_GROUPS[u[1]][2]:
-                G.gptq_quantize(ws[shp], f, QuantType.QInt4, "group", 128, True, False, 1.0, False, 128,
-                                "propagate", args.gptq_precision)
+        def solve(u):                                      # G2-G4 of one Hessian group
+            def job():
+                f = G.hinv_cholesky_upper(hs[u], 0.01, False, args.gptq_precision)
+                return [G.gptq_quantize(ws[shp], f, QuantType.QInt4, "group", 128, True, False, 1.0, False, 128,
+                                        "propagate", args.gptq_precision) for shp in GPTQ_GROUPS[u[1]][2]]
+            return job
+
+        mine = [i for i, u in enumerate(units) if owner[u] == rank]      # on the owner, side by side
+        pool.run([solve(units[i]) for i in mine], [costs[i] for i in mine])
         e3 = ev()
         return e0, e1, e2, e3
 
@@ -313,7 +319,7 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
         "workload": f"GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
                     f"{model}-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
                     f"{GPTQ_SAMPLES}x{GPTQ_SEQ} calibration tokens split over {world} rank(s)",
-        "precision": args.gptq_precision, "scaling": "strong", "n_gpus": world,
+        "precision": args.gptq_precision, "solve_streams": args.gptq_streams, "scaling": "strong", "n_gpus": world,
         "s_per_step": total_ms * 1e-3, "s_per_model_extrapolated": total_ms * 1e-3 * model_layers / layers,
         "extrapolation": f"x{model_layers / layers:g}: the {model_layers} layers are identical in shape",
         "hessian_s": hess_ms * 1e-3, "hessian_reduce_s": red_ms * 1e-3, "solve_s": solve_ms * 1e-3,
