@@ -496,6 +496,7 @@ def run_gpu_arm(args):
 
     from onnx_quantize_b200 import _lib
     from onnx_quantize_b200 import device_api as D
+    from onnx_quantize_b200._device import bind_host_to_gpu_numa_node
     from onnx_quantize_b200.core._dtypes import QuantType
     from onnx_quantize_b200.pipeline import RtnSpec, quantize_weights_bulk, result_bytes
 
@@ -507,6 +508,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
+    numa_cpus = bind_host_to_gpu_numa_node(local_rank) if world > 1 else None   # before any pinned allocation
 
     weights = make_weights(torch, device, args.layers, rank)
     elts = sum(w.numel() for w in weights)
@@ -616,7 +618,8 @@ def run_gpu_arm(args):
         "config": {"workload": WORKLOAD if args.layers == N_LAYERS else WORKLOAD + f" [{args.layers} layers]",
                    "elements_per_gpu": elts, "input_bytes_per_gpu": in_bytes,
                    "parallelism": f"{world} rank(s), one model-sized set each, no collective",
-                   "cache": "inputs (27.9 GB) larger than L2; no flush needed"},
+                   "cache": "inputs (27.9 GB) larger than L2; no flush needed",
+                   "host_cores_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": {"per_launch_bytes": 243.74e6, "algorithmic_bytes_same_launch": 266.3e6 * 4.0 / 4.535,
@@ -624,9 +627,10 @@ def run_gpu_arm(args):
                                          "profiles/r1_prof_rtn_details.txt): 235.2 MB read = the f32 weight once, "
                                          "8.5 MB written (the rest of the 29 MB result is still in L2 at kernel end)"},
                      "peak_source": peak_src,
-                     "kernel": "rtn_group_fused_kernel<128,MSE>",
-                     "note": "the MSE search is FP32/FP64-issue bound (20 candidates per element); "
-                             "the HBM-bound kernel is variants.cfg2a_no_mse"},
+                     "kernel": "rtn_group_mse4_kernel<128>",
+                     "note": "the MSE search is bound by the MUFU pipe and instruction issue (20 candidates x "
+                             "(quantize, dequantize, |d|^2.4) per element: ncu XU 73 %, issue 52 %), not by HBM; "
+                             "the HBM-bound kernel of the same path is variants.cfg2a_no_mse"},
         "variants": {"cfg2a_no_mse_clip0.9": {
             "ms_per_step": ms_plain, "value": world * in_bytes / (ms_plain * 1e-3) / 1e9, "unit": "GB/s",
             "roofline": {"bound": "hbm", "kernel": "rtn_group_nbits4_kernel<128>", "achieved": achieved_plain,

@@ -47,6 +47,37 @@ def to_device_f32(x, *, name: str = "array") -> torch.Tensor:
     return t.contiguous()
 
 
+def bind_host_to_gpu_numa_node(device_index: int | None = None) -> list[int] | None:
+    """Pin the calling process to the CPU cores local to the GPU's PCIe root (its NUMA node), so that
+    pinned host buffers allocated afterwards are first-touched on that node and host<->device
+    copies do not cross the socket interconnect — with one process per GPU on an 8-GPU box the
+    eight H2D streams otherwise all pull from one socket's memory.  Best effort: returns the core
+    list, or None when the topology cannot be read (no /sys entry, restricted container)."""
+    import os
+
+    try:
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        p = torch.cuda.get_device_properties(idx)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus: list[int] = []
+        for part in text.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.extend(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.append(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 - topology is optional information
+        return None
+
+
 @contextlib.contextmanager
 def inputs_resident(on: bool = True):
     """Within the context the caller asserts that every input tensor handed to the library was
