@@ -420,15 +420,16 @@ def run_small_variants(torch, device, peak):
     wq = ws[0]
     ms = time_ms(lambda: A.awq_search(wq, st, QuantType.QUInt4, "group", 128, False, False, clip_search=True),
                  iters=2, warm=1)
-    flops = 30 * 2.0 * k * k * wq.shape[1] * 3          # 30 Gram products, 3xTF32
+    flops = 30 * 2.0 * k * k * wq.shape[1] * 3          # 30 Gram products, 3 bf16 products each (BF16x3)
     out["awq_uint4_g128_q_proj"] = {
         "workload": "AWQ scale grid (20) + clip grid (10) for one 4096x4096 weight, uint4 g128, through the Gram "
                     "matrix (pre_passes/awq.py:121-184, :207-254); statistics accumulation timed separately",
         "ms_per_step": ms, "stats_ms_per_8192_tokens": ms_stats,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tn_tc_kernel", "achieved": flops / (ms * 1e-3) / 1e12,
-                     "unit": "TFLOP/s", "peak": 696.95, "frac": flops / (ms * 1e-3) / 1e12 / 696.95,
-                     "note": "tf32 MMA flops of the 30 (K,K)x(K,N) products / whole search time (the search also "
-                             "runs 30 RTN parameter passes, residual and dot kernels)"}}
+        "roofline": {"bound": "tensor", "kernel": "dense_bf16x3_kernel", "achieved": flops / (ms * 1e-3) / 1e12,
+                     "unit": "TFLOP/s", "peak": 1393.9, "frac": flops / (ms * 1e-3) / 1e12 / 1393.9,
+                     "note": "bf16 MMA flops of the 30 (K,K)x(K,N) products / whole search time (the search also "
+                             "runs 30 RTN parameter passes, residual, plane-split and dot kernels — about half "
+                             "of the time); peak = measured sustained bf16"}}
     del flush
     return out
 
@@ -480,14 +481,16 @@ def run_cfg3_mlp(torch, dist, device, world, rank):
     del data, layers
     torch.cuda.empty_cache()
     return {"workload": "cfg3: static W8A8 of a 2-layer 4096-wide Gemm MLP, 100x512x4096 f32 calibration samples in 10 "
-                        f"batches sharded over {world} rank(s): on-device forward (tcgen05 3xTF32), min/max of 4 "
+                        f"batches sharded over {world} rank(s): on-device forward (tcgen05 BF16x3), min/max of 4 "
                         "activation tensors, NCCL min/max all-reduce, uint8 activation parameters, int8 per-channel "
                         "weights, int32 biases", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
             "calibration_bytes": 100 * 512 * k * 4, "value": 100 * 512 * k * 4 / (ms * 1e-3) / 1e9, "unit": "GB/s",
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_tc_kernel", "unit": "TFLOP/s",
-                         "achieved": 2 * 2.0 * 51200 * k * k * 3 / world / (ms * 1e-3) / 1e12, "peak": 696.95,
-                         "frac": 2 * 2.0 * 51200 * k * k * 3 / world / (ms * 1e-3) / 1e12 / 696.95,
-                         "note": "tf32 MMA flops of the two forward products per GPU / whole step"}}
+            "roofline": {"bound": "tensor", "kernel": "dense_bf16x3_kernel", "unit": "TFLOP/s",
+                         "achieved": 2 * 2.0 * 51200 * k * k * 3 / world / (ms * 1e-3) / 1e12, "peak": 1393.9,
+                         "frac": 2 * 2.0 * 51200 * k * k * 3 / world / (ms * 1e-3) / 1e12 / 1393.9,
+                         "note": "bf16 MMA flops (3 products of the BF16x3 split) of the two forward products per "
+                                 "GPU / whole step (splits, min/max passes, weight and bias quantization included); "
+                                 "peak = measured sustained bf16"}}
 
 
 def run_gpu_arm(args):

@@ -330,6 +330,22 @@ int b200q_scale_rows(const float* W, int64_t K, int64_t N, const float* row_scal
  * (K x tokens) so that every layer is a b200q_gemm_tn: Y^T = gemm_tn(W, X^T).
  *   b200q_transpose  out (cols x rows) = in (rows x cols)^T — the calibration batch into that layout
  *   b200q_bias_act   Y (N x T) <- act(Y + bias[n]); bias may be NULL; relu 0/1 */
+/* Token-major dense layer on tcgen05 through the BF16x3 split (x = bf16(x) + bf16(x - bf16(x)),
+ * three kind::f16 products, fp32 accumulate):  Y (M x N, row stride ldy) = act(alpha * A · B^T + bias)
+ * with A = X (M x K) and B = W^T (N x K).  Operands are passed as pre-split bf16 plane buffers of
+ * b200q_dense_planes_bytes(rows, K) bytes: b200q_dense_split_rows for a row-major (rows x K)
+ * matrix (activations; a symmetric matrix), b200q_dense_split_transposed for a (K x N) weight
+ * (written as N x K, once per layer).  N % 32 == 0, K % 4 == 0; B200Q_ERR_UNSUPPORTED otherwise
+ * (callers fall back to b200q_gemm_tn).  bias (N floats) and relu are optional. */
+size_t b200q_dense_planes_bytes(int64_t rows, int64_t K);
+int b200q_dense_split_rows(const float* X, int64_t rows, int64_t K, void* planes, size_t planes_bytes,
+                           b200q_stream_t stream);
+int b200q_dense_split_transposed(const float* W, int64_t K, int64_t N, void* planes, size_t planes_bytes,
+                                 b200q_stream_t stream);
+int b200q_dense_forward_planes(const void* a_planes, int64_t M, const void* b_planes, int64_t N, int64_t K,
+                               float alpha, const float* bias, int relu, float* Y, int64_t ldy,
+                               b200q_stream_t stream);
+
 int b200q_transpose(const float* in, int64_t rows, int64_t cols, float* out, b200q_stream_t stream);
 int b200q_bias_act(float* Y, int64_t N, int64_t T, const float* bias, int relu, b200q_stream_t stream);
 

@@ -96,6 +96,10 @@ _OPTIONAL_SIGNATURES = {
     "b200q_row_abs_max": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
     "b200q_scale_rows": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _ptr]),
     "b200q_transpose": (_i32, [_ptr, _i64, _i64, _ptr, _ptr]),
+    "b200q_dense_planes_bytes": (_sz, [_i64, _i64]),
+    "b200q_dense_split_rows": (_i32, [_ptr, _i64, _i64, _ptr, _sz, _ptr]),
+    "b200q_dense_split_transposed": (_i32, [_ptr, _i64, _i64, _ptr, _sz, _ptr]),
+    "b200q_dense_forward_planes": (_i32, [_ptr, _i64, _ptr, _i64, _i64, _f32, _ptr, _i32, _ptr, _i64, _ptr]),
     "b200q_bias_act": (_i32, [_ptr, _i64, _i64, _ptr, _i32, _ptr]),
     "b200q_gemm_tn": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _f32, _i32, _i32,
                               _ptr]),

@@ -4,10 +4,12 @@ The reference calibrates by running the ONNX model in an ONNX Runtime session, k
 activation of every batch in host lists, and feeding them to the calibrator afterwards
 (``core/_calibration/calibrate.py``: ``_prepare_calibration_data`` :150-179, ``_collect_activations``
 :204-251, ``_set_qparams`` :254-285).  For the chains it targets (MatMul / Gemm nodes) the same
-statistics come from a forward pass on the device: each calibration batch is transposed once to
-feature-major, every layer is one tensor-core ``gemm_tn`` (+ bias / ReLU), the calibrator's
-streaming min/max kernels read the activations where they are, and nothing is ever copied to the
-host or kept — only ``(min, max)`` per tensor survives.  With several ranks the batches are
+statistics come from a forward pass on the device: every layer is one tensor-core product — the
+token-major BF16x3 kernel of ``dense.py`` (bias / ReLU in its epilogue, the output is the next
+layer's input as it is) or, for shapes it does not take and for ``precision != "bf16x3"``, the
+feature-major ``gemm_tn`` route — the calibrator's streaming min/max kernels read the activations
+where they are, and nothing is ever copied to the host or kept: only ``(min, max)`` per tensor
+survives.  With several ranks the batches are
 sharded (``parallel.calibration``) and the ranges combined with one all-reduce.
 """
 from __future__ import annotations
@@ -19,6 +21,7 @@ import torch
 
 from onnx_quantize_b200 import _device as dev
 from onnx_quantize_b200 import _lib
+from onnx_quantize_b200 import dense as DN
 from onnx_quantize_b200 import gptq_device as G
 from onnx_quantize_b200.core._algorithms.utils import _compute_qparams
 from onnx_quantize_b200.core._calibration.base import CalibrationParams
@@ -59,7 +62,7 @@ def _forward_feature_major(xt: torch.Tensor, w: torch.Tensor, bias, relu: bool, 
 
 
 def calibrate_mlp(layers, calibration_data, qconfig, params: CalibrationParams | None = None,
-                  precision: str = "tf32x3", group=None) -> dict:
+                  precision: str = "bf16x3", group=None) -> dict:
     """Ranges and quantization parameters of every layer's input (and output) activation.
 
     Returns ``{layer.name: {"input_scale", "input_zero_point", "input_range"[, "output_*"]}}`` —
@@ -78,10 +81,23 @@ def calibrate_mlp(layers, calibration_data, qconfig, params: CalibrationParams |
     rank, n_ranks = world()
     mine = PC.shard_batches(batches.shape[0], rank, n_ranks)
     names = []
+    token_major = precision == "bf16x3" and all(DN.supported(int(w.shape[0]), int(w.shape[1])) for w in ws)
+    w_planes = [DN.Planes.of_weight(w) for w in ws] if token_major else None
+    x_planes: dict = {}
     for b in mine:
         x = dev.to_device_f32(batches[b])
         k0 = int(x.shape[-1])
         x2 = x.reshape(-1, k0)
+        if token_major:
+            for li, (layer, bias) in enumerate(zip(layers, bs)):
+                if in_args is not None:
+                    calibrator.collect(f"{layer.name}/input", x2)
+                key = (int(x2.shape[0]), int(x2.shape[1]))
+                x_planes[key] = DN.Planes.of_rows(x2, x_planes.get(key))      # one plane buffer per shape, reused
+                x2 = DN.forward_planes(x_planes[key], w_planes[li], 1.0, bias, layer.activation == "relu")
+                if out_args is not None:
+                    calibrator.collect(f"{layer.name}/output", x2)
+            continue
         xt = torch.empty((k0, x2.shape[0]), dtype=torch.float32, device=device)
         _lib.check(lib.b200q_transpose(x2.data_ptr(), int(x2.shape[0]), k0, xt.data_ptr(), dev.stream_ptr()),
                    "b200q_transpose")

@@ -203,7 +203,8 @@ size_t b200q_awq_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t gro
   if (rtn == 0) return 0;
   const int64_t rows = strategy == B200Q_TENSOR ? 1 : N * make_map(K, N, strategy, group_size).G;
   return align_up(rtn, 256) + 3 * align_up((size_t)K * N * 4, 256) + align_up((size_t)rows * 4, 256) +
-         align_up((size_t)rows, 256) + 2 * align_up((size_t)rows * 4, 256);
+         align_up((size_t)rows, 256) + 2 * align_up((size_t)rows * 4, 256) +
+         align_up(b200q_dense_planes_bytes(K, K), 256) + align_up(b200q_dense_planes_bytes(N, K), 256);   // BF16x3 route
 }
 
 int b200q_awq_weight_scale(const float* W, int64_t K, int64_t N, int strategy, int64_t group_size,
@@ -240,7 +241,10 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
                    double tokens, int qtype, int strategy, int64_t group_size, int symmetric,
                    int reduce_range, double clip_ratio, int precision, double* loss_out, void* workspace,
                    size_t workspace_bytes, b200q_stream_t stream) {
-  if (precision == B200Q_BF16X3) precision = B200Q_TF32X3;   // BF16x3 is a Hessian-only mode; dense solves use TF32x3
+  // BF16x3: the product with the Gram matrix goes through the token-major dense kernel (G is
+  // symmetric, so its rows are the K-major row operand; the residual D is split transposed)
+  const bool dense_route = precision == B200Q_BF16X3 && N % 32 == 0 && K % 4 == 0 && ((uintptr_t)gram % 16 == 0);
+  if (precision == B200Q_BF16X3) precision = B200Q_TF32X3;
   cudaStream_t st = (cudaStream_t)stream;
   B200Q_REQUIRE(W && gram && loss_out && K > 0 && N > 0 && tokens > 0, B200Q_ERR_INVALID_ARG, "bad argument");
   QSpec qs;
@@ -272,9 +276,22 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
   if (rc != B200Q_OK) return rc;
   awq_residual_kernel<<<grid_for(K * N), 256, 0, st>>>(W, m, qs, row_scale, scale, zp, D);  // :167-175
   B200Q_LAUNCH_OK();
-  GemmTN g{gram, K, D, N, P, N, K, K, N, 1.0f, 0, 0, 0, precision};                    // G is symmetric: G^T D
-  rc = gemm_tn(g, st);
-  if (rc != B200Q_OK) return rc;
+  if (dense_route) {
+    const size_t gp_bytes = align_up(b200q_dense_planes_bytes(K, K), 256), dp_bytes = b200q_dense_planes_bytes(N, K);
+    char* gp = base + rtn_bytes + 3 * mat + align_up((size_t)rows * 4, 256) + align_up((size_t)rows, 256) +
+               2 * align_up((size_t)rows * 4, 256);
+    char* dp = gp + gp_bytes;
+    rc = b200q_dense_split_rows(gram, K, K, gp, gp_bytes, stream);
+    if (rc != B200Q_OK) return rc;
+    rc = b200q_dense_split_transposed(D, K, N, dp, dp_bytes, stream);
+    if (rc != B200Q_OK) return rc;
+    rc = b200q_dense_forward_planes(gp, K, dp, N, K, 1.0f, nullptr, 0, P, N, stream);   // P = G D
+    if (rc != B200Q_OK) return rc;
+  } else {
+    GemmTN g{gram, K, D, N, P, N, K, K, N, 1.0f, 0, 0, 0, precision};                  // G is symmetric: G^T D
+    rc = gemm_tn(g, st);
+    if (rc != B200Q_OK) return rc;
+  }
   B200Q_CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(double), st));
   awq_dot_kernel<<<kNumSMs * 4, 256, 0, st>>>(P, D, K * N, 1.0 / (tokens * (double)N), loss_out);  // :176-178
   B200Q_LAUNCH_OK();

@@ -27,6 +27,7 @@ OPTIONAL = {
     "awq.cu": ["-fmad=false"],
     "hqq.cu": ["-fmad=false"],
     "mlp.cu": [],
+    "dense_bf16.cu": [],
 }
 
 COMMON = [
