@@ -511,7 +511,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
-    numa_cpus = bind_host_to_gpu_numa_node(local_rank) if world > 1 else None   # before any pinned allocation
+    numa_cpus = bind_host_to_gpu_numa_node(local_rank)      # before any pinned allocation: H2D from the local node
 
     weights = make_weights(torch, device, args.layers, rank)
     elts = sum(w.numel() for w in weights)
