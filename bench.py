@@ -631,6 +631,8 @@ def run_gpu_arm(args):
                                          "8.5 MB written (the rest of the 29 MB result is still in L2 at kernel end)"},
                      "peak_source": peak_src,
                      "kernel": "rtn_group_mse4_kernel<128>",
+                     "compute_pipes_ncu": {"xu_mufu_busy_pct": 73, "issue_active_pct": 52,
+                                           "source": "profiles/r1_prof_rtn_final_details.txt (4096x14336 launch, 0.82 ms)"},
                      "note": "the MSE search is bound by the MUFU pipe and instruction issue (20 candidates x "
                              "(quantize, dequantize, |d|^2.4) per element: ncu XU 73 %, issue 52 %), not by HBM; "
                              "the HBM-bound kernel of the same path is variants.cfg2a_no_mse"},
