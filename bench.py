@@ -583,9 +583,23 @@ def run_gpu_arm(args):
             t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t[0])
+        # what the link itself delivers on this box: plain pinned -> device copies of the same buffers
+        dst = [torch.empty_like(g_, device=device) for g_ in gens]
+        for g_, d_ in zip(gens, dst):
+            d_.copy_(g_, non_blocking=True)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            for g_, d_ in zip(gens, dst):
+                d_.copy_(g_, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 4 * sum(g_.numel() * 4 for g_ in gens) / (time.perf_counter() - t0) / 1e9
+        del dst
         e2e = {"value": world * in_bytes / e2e_s / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                "ms_per_step": e2e_s * 1e3,
+               "pcie_h2d_gbs_measured_per_gpu": h2d_gbs,
+               "frac_of_pcie_h2d": (in_bytes / e2e_s / 1e9) / h2d_gbs,
                "api": "onnx_quantize_b200.pipeline.quantize_weights_bulk (pinned host weights in, host results out)"}
 
     small = run_small_variants(torch, device, measured_peaks()[0]) if rank == 0 else None
