@@ -54,7 +54,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gptq", action="store_true")
-    p.add_argument("--gptq-layers", type=int, default=4,
+    p.add_argument("--gptq-layers", type=int, default=8,
                    help="Llama-3-8B-shaped layers in the GPTQ sample (the model has 32)")
     p.add_argument("--gptq-precision", default="bf16x3", choices=["tf32", "tf32x3", "bf16x3"])
     p.add_argument("--gptq-streams", type=int, default=8,
