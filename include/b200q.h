@@ -304,9 +304,8 @@ int b200q_awq_loss(const float* W, int64_t K, int64_t N, const float* row_scale,
  *   out_zp         f32 per parameter row (HQQ zero points are floats: hqq.py:77)
  *   out_best_iter  optional device int32: index of the returned iterate (-1: the RTN zero point)
  *   out_errors     optional device f64[iters]: the global mean error of every iteration
- * Parity: float32 op order and NumPy's pairwise row sums reproduced; `np.power` is evaluated in
- * float64 and rounded once (NumPy's own result is host-dependent), so zero points agree to the
- * last bits, not bit for bit.
+ * Parity: float32 op order and NumPy's pairwise row sums reproduced; `np.power` (host-dependent in
+ * NumPy itself) is CUDA's float32 powf, so zero points agree to the last bits, not bit for bit.
  * ------------------------------------------------------------------------------------------ */
 size_t b200q_hqq_workspace_bytes(int64_t K, int64_t N, int64_t group_size, int mse, int iters);
 int b200q_hqq_quantize(const float* W, int64_t K, int64_t N, int qtype, int64_t group_size, int reduce_range,

@@ -15,7 +15,7 @@
 // are weak scalars, i.e. float32).  Row means use NumPy's pairwise summation order for a
 // contiguous row (leaves of <= 128 elements with eight strided accumulators, the same split
 // recursion); the leaf/merge program is built on the host (it only depends on gs).  `np.power` is
-// host-dependent (SVML / glibc); the device evaluates it in float64 and rounds once.  The global
+// host-dependent (SVML / glibc, 1 ulp apart); the device uses float32 powf.  The global
 // error is accumulated in float64 in a fixed order (the reference: float32 pairwise) — it only
 // feeds comparisons between consecutive iterations.
 #include <vector>
@@ -81,7 +81,16 @@ __global__ void __launch_bounds__(kHqqThreads) hqq_iterate_kernel(HqqArgs a, Hqq
   const float inv = __fdiv_rn(1.0f, s);                 // hqq.py:122: scale = 1.0 / scale
   float zp = live ? (float)a.zp0[row] : 0.0f;
   double beta = a.beta;
+#ifdef B200Q_HQQ_POW_F64
   const double expo = (double)a.lp_minus_1;
+#define HQQ_POW(x) ((float)pow((double)(x), expo))
+#else
+  // float32 powf (CUDA: <= 2 ulp here), the accuracy class of NumPy's own host-dependent np.power
+  // (SVML and glibc differ from each other by 1 ulp on 21 % / 0.06 % of the inputs); the float64
+  // evaluation it replaced kept the FP64 pipe 46 % busy (ncu) for no gain in parity
+  const float expo = a.lp_minus_1;
+#define HQQ_POW(x) powf((x), expo)
+#endif
   const int64_t rows = a.N * a.G;
   const int n_cta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
   for (int it = 0; it < a.iters; ++it) {
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(kHqqThreads) hqq_iterate_kernel(HqqArgs a, Hqq
           const float ad = fabsf(d);
           err += (double)ad;
           // _shrink_op, hqq.py:103-104
-          const float p = (float)pow((double)__fadd_rn(ad, 1e-8f), expo);
+          const float p = HQQ_POW(__fadd_rn(ad, 1e-8f));
           const float relu = fmaxf(0.0f, __fsub_rn(ad, __fmul_rn(inv_beta, p)));
           const float sign = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : d);   // np.sign: 0 -> 0, nan -> nan
           const float we = __fmul_rn(sign, relu);
