@@ -229,7 +229,8 @@ int b200q_awq_weight_scale(const float* W, int64_t K, int64_t N, int strategy, i
     B200Q_CUDA_OK(cudaMemsetAsync(enc_min, 0xFF, (size_t)rows * 4, st));
     B200Q_CUDA_OK(cudaMemsetAsync(enc_max, 0x00, (size_t)rows * 4, st));
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kStatRowsPerCta));
-    rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, enc_min, enc_max);
+    if (slab_stats_ok(W, m)) launch_rowstats_slab(W, m, enc_min, enc_max, st);
+    else rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, enc_min, enc_max);
   }
   B200Q_LAUNCH_OK();
   awq_weight_scale_kernel<<<(unsigned)K, 256, 0, st>>>(W, m, enc_min, enc_max, out);

@@ -136,8 +136,12 @@ static int launch_rowstats(const float* W, const RowMap& m, int64_t rows, RtnWor
   } else {
     B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_min, 0xFF, (size_t)rows * 4, st));
     B200Q_CUDA_OK(cudaMemsetAsync(ws.enc_max, 0x00, (size_t)rows * 4, st));
-    dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)ceil_div(m.K, kStatRowsPerCta));
-    rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, ws.enc_min, ws.enc_max);
+    if (slab_stats_ok(W, m)) {
+      launch_rowstats_slab(W, m, ws.enc_min, ws.enc_max, st);
+    } else {
+      dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)ceil_div(m.K, kStatRowsPerCta));
+      rowstats_cols_kernel<<<grid, 128, 0, st>>>(W, m, ws.enc_min, ws.enc_max);
+    }
   }
   B200Q_LAUNCH_OK();
   return B200Q_OK;
@@ -348,8 +352,13 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
 
   if (!fused || mse) {
     // generic quantize (+ pack): the only route when !fused, the conditional fix-up when fused
-    quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, st>>>(W, m, qs, out_scale, zp_rows,
-                                                                  kn_dst, fixup_ctl);
+    if (fixup_ctl == nullptr && slab_quant_ok(W, m, kn_dst)) {
+      dim3 grid((unsigned)ceil_div(N, 128), (unsigned)(K / kSlabCtaRows));
+      quantize_slab_kernel<<<grid, 256, 0, st>>>(W, m, qs, out_scale, zp_rows, kn_dst);
+    } else {
+      quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, st>>>(W, m, qs, out_scale, zp_rows,
+                                                                    kn_dst, fixup_ctl);
+    }
     B200Q_LAUNCH_OK();
     if (layout == B200Q_PACKED_FLAT) {
       pack4_flat_kernel<<<elementwise_grid((K * N + 1) / 2), 256, 0, st>>>(
@@ -507,8 +516,14 @@ int b200q_quantize_with_qparams(const float* W, int64_t K, int64_t N, int qtype,
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
-      W, s.map, qs, scale, (const unsigned char*)zp, (unsigned char*)out_codes, nullptr);
+  if (slab_quant_ok(W, s.map, out_codes)) {
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)(K / kSlabCtaRows));
+    quantize_slab_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, s.map, qs, scale, (const unsigned char*)zp,
+                                                                 (unsigned char*)out_codes);
+  } else {
+    quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(
+        W, s.map, qs, scale, (const unsigned char*)zp, (unsigned char*)out_codes, nullptr);
+  }
   B200Q_LAUNCH_OK();
   return B200Q_OK;
 }

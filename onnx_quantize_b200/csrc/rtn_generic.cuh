@@ -58,6 +58,119 @@ static __global__ void __launch_bounds__(128) rowstats_cols_kernel(const float* 
   atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
 }
 
+// ---- tuned variants for N % 4 == 0, 16-byte aligned W and groups that are multiples of 256 rows
+// (CHANNEL with K % 256 == 0, large groups).  A thread owns four consecutive columns (one 128-bit
+// load per row) and a 32-row slab; a CTA = 8 warps = 128 columns x 256 rows, all in one group, so
+// its warps fold through shared memory and issue ONE atomic pair per column.  The scalar kernels
+// above (one 4-byte load in flight per thread, a 64-bit division per row) ran at 5-8 % of the HBM
+// roofline (tools/prof_generic.py); these at the rate of the per-tensor route.
+constexpr int kSlabRows = 32;
+constexpr int kSlabCtaRows = 8 * kSlabRows;
+
+template <bool KEEP>
+static __global__ void __launch_bounds__(256, 4) rowstats_slab_kernel(const float* __restrict__ W, RowMap m,
+                                                                      unsigned int* __restrict__ enc_min,
+                                                                      unsigned int* __restrict__ enc_max) {
+  __shared__ float4 s_mn[8][32], s_mx[8][32];
+  const uint64_t policy = l2_policy_evict_last();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = ((int64_t)blockIdx.x * 32 + lane) * 4;
+  const int64_t k0 = (int64_t)blockIdx.y * kSlabCtaRows + warp * kSlabRows;
+  float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (n < m.N) {
+#pragma unroll
+    for (int b = 0; b < kSlabRows; b += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t k = k0 + b + u;
+        const float* src = W + (k < m.K ? k : m.K - 1) * m.N + n;     // past the end: re-reads the last row (harmless)
+        v[u] = KEEP ? ldg_keep4(src, policy) : ldg_stream4(src);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        mn.x = fminf(mn.x, v[u].x); mn.y = fminf(mn.y, v[u].y); mn.z = fminf(mn.z, v[u].z); mn.w = fminf(mn.w, v[u].w);
+        mx.x = fmaxf(mx.x, v[u].x); mx.y = fmaxf(mx.y, v[u].y); mx.z = fmaxf(mx.z, v[u].z); mx.w = fmaxf(mx.w, v[u].w);
+      }
+    }
+  }
+  s_mn[warp][lane] = mn; s_mx[warp][lane] = mx;
+  __syncthreads();
+  if (warp == 0 && n < m.N) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 a = s_mn[w][lane], b = s_mx[w][lane];
+      mn.x = fminf(mn.x, a.x); mn.y = fminf(mn.y, a.y); mn.z = fminf(mn.z, a.z); mn.w = fminf(mn.w, a.w);
+      mx.x = fmaxf(mx.x, b.x); mx.y = fmaxf(mx.y, b.y); mx.z = fmaxf(mx.z, b.z); mx.w = fmaxf(mx.w, b.w);
+    }
+    const int64_t g = ((int64_t)blockIdx.y * kSlabCtaRows) / m.gs;   // gs % 256 == 0: one group per CTA
+    const float lo[4] = {mn.x, mn.y, mn.z, mn.w}, hi[4] = {mx.x, mx.y, mx.z, mx.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      atomicMin(&enc_min[(n + c) * m.G + g], float_to_ordered(lo[c]));
+      atomicMax(&enc_max[(n + c) * m.G + g], float_to_ordered(hi[c]));
+    }
+  }
+}
+
+// A4 with given per-row parameters, KN_BYTES output, same slab mapping; the slabs are walked from
+// the END of the matrix so that the tail of the statistics pass is still in L2
+static __global__ void __launch_bounds__(256, 4) quantize_slab_kernel(
+    const float* __restrict__ W, RowMap m, QSpec qs, const float* __restrict__ scale,
+    const unsigned char* __restrict__ zp, unsigned char* __restrict__ out) {
+  const uint64_t demote = l2_policy_evict_first();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = ((int64_t)blockIdx.x * 32 + lane) * 4;
+  const int64_t slab_cta = (int64_t)gridDim.y - 1 - blockIdx.y;
+  const int64_t k0 = slab_cta * kSlabCtaRows + warp * kSlabRows;
+  if (n >= m.N || k0 >= m.K) return;
+  const int64_t g = k0 / m.gs;
+  float sc[4];
+  int z[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int64_t r = (n + c) * m.G + g;
+    sc[c] = scale[r];
+    z[c] = decode_code(zp[r], qs);
+  }
+#pragma unroll
+  for (int b = 0; b < kSlabRows; b += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t k = k0 + b + u;
+      v[u] = ldg_keep4(W + (k < m.K ? k : m.K - 1) * m.N + n, demote);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t k = k0 + b + u;
+      if (k < m.K) {
+        const unsigned int q0 = encode_code(quant_code(v[u].x, sc[0], z[0], qs.qmin, qs.qmax), qs);
+        const unsigned int q1 = encode_code(quant_code(v[u].y, sc[1], z[1], qs.qmin, qs.qmax), qs);
+        const unsigned int q2 = encode_code(quant_code(v[u].z, sc[2], z[2], qs.qmin, qs.qmax), qs);
+        const unsigned int q3 = encode_code(quant_code(v[u].w, sc[3], z[3], qs.qmin, qs.qmax), qs);
+        *reinterpret_cast<unsigned int*>(out + k * m.N + n) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+      }
+    }
+  }
+}
+
+static inline bool slab_stats_ok(const float* W, const RowMap& m) {
+  return m.strategy != B200Q_TENSOR && m.N % 4 == 0 && m.gs % kSlabCtaRows == 0 && m.K % m.gs == 0 &&
+         ((uintptr_t)W % 16 == 0) && m.K / kSlabCtaRows <= 65535;
+}
+static inline bool slab_quant_ok(const float* W, const RowMap& m, const void* out) {
+  return slab_stats_ok(W, m) && ((uintptr_t)out % 4 == 0);
+}
+// min/max of every parameter row into enc_min / enc_max (pre-initialised by the caller)
+static inline void launch_rowstats_slab(const float* W, const RowMap& m, unsigned int* enc_min, unsigned int* enc_max,
+                                        cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)(m.K / kSlabCtaRows));
+  if (m.K * m.N * 4 <= (96ll << 20)) rowstats_slab_kernel<true><<<grid, 256, 0, st>>>(W, m, enc_min, enc_max);
+  else rowstats_slab_kernel<false><<<grid, 256, 0, st>>>(W, m, enc_min, enc_max);
+}
+
 // ---- encoded min/max -> (scale, zp) per row: A2 tail (clip, include zero) + A3 -----------------
 static __global__ void qparams_from_stats_kernel(const unsigned int* __restrict__ enc_min,
                                           const unsigned int* __restrict__ enc_max, int64_t rows,
