@@ -353,7 +353,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
   if (!fused || mse) {
     // generic quantize (+ pack): the only route when !fused, the conditional fix-up when fused
     if (fixup_ctl == nullptr && slab_quant_ok(W, m, kn_dst)) {
-      dim3 grid((unsigned)ceil_div(N, 128), (unsigned)(K / kSlabCtaRows));
+      dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kSlabCtaRows));
       quantize_slab_kernel<<<grid, 256, 0, st>>>(W, m, qs, out_scale, zp_rows, kn_dst);
     } else {
       quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, st>>>(W, m, qs, out_scale, zp_rows,
@@ -517,7 +517,7 @@ int b200q_quantize_with_qparams(const float* W, int64_t K, int64_t N, int qtype,
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
   if (slab_quant_ok(W, s.map, out_codes)) {
-    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)(K / kSlabCtaRows));
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kSlabCtaRows));
     quantize_slab_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, s.map, qs, scale, (const unsigned char*)zp,
                                                                  (unsigned char*)out_codes);
   } else {

@@ -58,10 +58,11 @@ static __global__ void __launch_bounds__(128) rowstats_cols_kernel(const float* 
   atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
 }
 
-// ---- tuned variants for N % 4 == 0, 16-byte aligned W and groups that are multiples of 256 rows
-// (CHANNEL with K % 256 == 0, large groups).  A thread owns four consecutive columns (one 128-bit
-// load per row) and a 32-row slab; a CTA = 8 warps = 128 columns x 256 rows, all in one group, so
-// its warps fold through shared memory and issue ONE atomic pair per column.  The scalar kernels
+// ---- tuned variants for N % 4 == 0, 16-byte aligned W and groups that are multiples of 32 rows.
+// A thread owns four consecutive columns (one 128-bit load per row) and a 32-row slab; a CTA =
+// 8 warps = 128 columns x 256 rows.  When the group is a multiple of 256 rows (CHANNEL, large
+// groups) the whole CTA is in one group: its warps fold through shared memory and issue ONE atomic
+// pair per column; smaller groups: one pair per warp and column.  The scalar kernels
 // above (one 4-byte load in flight per thread, a 64-bit division per row) ran at 5-8 % of the HBM
 // roofline (tools/prof_generic.py); these at the rate of the per-tensor route.
 constexpr int kSlabRows = 32;
@@ -78,7 +79,8 @@ static __global__ void __launch_bounds__(256, 4) rowstats_slab_kernel(const floa
   const int64_t k0 = (int64_t)blockIdx.y * kSlabCtaRows + warp * kSlabRows;
   float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
   float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  if (n < m.N) {
+  const bool live = n < m.N && k0 < m.K;       // K % 32 == 0: a slab is all in or all out
+  if (live) {
 #pragma unroll
     for (int b = 0; b < kSlabRows; b += 8) {
       float4 v[8];
@@ -94,6 +96,18 @@ static __global__ void __launch_bounds__(256, 4) rowstats_slab_kernel(const floa
         mx.x = fmaxf(mx.x, v[u].x); mx.y = fmaxf(mx.y, v[u].y); mx.z = fmaxf(mx.z, v[u].z); mx.w = fmaxf(mx.w, v[u].w);
       }
     }
+  }
+  if (m.gs % kSlabCtaRows != 0) {              // groups of 32..224 rows: every warp has its own group
+    if (live) {
+      const int64_t g = k0 / m.gs;
+      const float lo[4] = {mn.x, mn.y, mn.z, mn.w}, hi[4] = {mx.x, mx.y, mx.z, mx.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicMin(&enc_min[(n + c) * m.G + g], float_to_ordered(lo[c]));
+        atomicMax(&enc_max[(n + c) * m.G + g], float_to_ordered(hi[c]));
+      }
+    }
+    return;
   }
   s_mn[warp][lane] = mn; s_mx[warp][lane] = mx;
   __syncthreads();
@@ -157,8 +171,8 @@ static __global__ void __launch_bounds__(256, 4) quantize_slab_kernel(
 }
 
 static inline bool slab_stats_ok(const float* W, const RowMap& m) {
-  return m.strategy != B200Q_TENSOR && m.N % 4 == 0 && m.gs % kSlabCtaRows == 0 && m.K % m.gs == 0 &&
-         ((uintptr_t)W % 16 == 0) && m.K / kSlabCtaRows <= 65535;
+  return m.strategy != B200Q_TENSOR && m.N % 4 == 0 && m.gs % kSlabRows == 0 && m.K % m.gs == 0 &&
+         ((uintptr_t)W % 16 == 0) && ceil_div(m.K, kSlabCtaRows) <= 65535;
 }
 static inline bool slab_quant_ok(const float* W, const RowMap& m, const void* out) {
   return slab_stats_ok(W, m) && ((uintptr_t)out % 4 == 0);
@@ -166,7 +180,7 @@ static inline bool slab_quant_ok(const float* W, const RowMap& m, const void* ou
 // min/max of every parameter row into enc_min / enc_max (pre-initialised by the caller)
 static inline void launch_rowstats_slab(const float* W, const RowMap& m, unsigned int* enc_min, unsigned int* enc_max,
                                         cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)(m.K / kSlabCtaRows));
+  dim3 grid((unsigned)ceil_div(m.N, 128), (unsigned)ceil_div(m.K, kSlabCtaRows));
   if (m.K * m.N * 4 <= (96ll << 20)) rowstats_slab_kernel<true><<<grid, 256, 0, st>>>(W, m, enc_min, enc_max);
   else rowstats_slab_kernel<false><<<grid, 256, 0, st>>>(W, m, enc_min, enc_max);
 }
