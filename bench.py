@@ -647,6 +647,13 @@ def run_gpu_arm(args):
                      "kernel": "rtn_group_mse4_kernel<128>",
                      "compute_pipes_ncu": {"xu_mufu_busy_pct": 73, "issue_active_pct": 52,
                                            "source": "profiles/r1_prof_rtn_final_details.txt (4096x14336 launch, 0.82 ms)"},
+                     # the bound that actually applies: 2 MUFU operations (lg2, ex2) per candidate-element,
+                     # 20 candidates, 16 MUFU lanes per SM and clock
+                     "mufu_roofline": {"ops_per_step": 2.0 * 20 * elts,
+                                       "achieved_gops": 2.0 * 20 * elts / (ms_mse * 1e-3) / 1e9,
+                                       "peak_gops": 148 * 16 * 1.965,
+                                       "frac": 2.0 * 20 * elts / (ms_mse * 1e-3) / 1e9 / (148 * 16 * 1.965),
+                                       "peak_source": "148 SMs x 16 MUFU lanes x 1.965 GHz (nominal)"},
                      "note": "the MSE search is bound by the MUFU pipe and instruction issue (20 candidates x "
                              "(quantize, dequantize, |d|^2.4) per element: ncu XU 73 %, issue 52 %), not by HBM; "
                              "the HBM-bound kernel of the same path is variants.cfg2a_no_mse"},
