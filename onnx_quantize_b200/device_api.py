@@ -66,8 +66,21 @@ def num_rows(k: int, n: int, strategy: int, group_size) -> int:
     return n * resolve_group(k, strategy, group_size)[1]
 
 
+def output_shapes(k: int, n: int, quant_type, strategy, group_size=-1, layout="kn"):
+    """((codes shape, uint8), (scale shape, float32), (zp shape, uint8)) of ``rtn_quantize``."""
+    qt, st = _qt(quant_type), _strategy(strategy)
+    gs, g = resolve_group(k, st, group_size)
+    rows = num_rows(k, n, st, group_size)
+    bits = 4 if qt in (0, 1) else 8
+    if layout == "kn":
+        return (k, n), (rows,), (rows,)
+    if layout == "packed_flat":
+        return ((k * n + 1) // 2,), (rows,), (rows,)
+    return (n, g, gs * bits // 8), (n, g), (n, (g + 1) // 2 if (bits == 4 and g > 1) else g)
+
+
 def rtn_quantize(w: torch.Tensor, quant_type, strategy, group_size=-1, is_symmetric=False,
-                 reduce_range=False, clip_ratio=1.0, mse=False, layout="kn", return_info=False):
+                 reduce_range=False, clip_ratio=1.0, mse=False, layout="kn", return_info=False, out=None):
     """RTN (+MSE) quantization of one (K,N) float32 weight on the GPU.
 
     Returns ``(codes, scale, zp)`` as CUDA tensors:
@@ -76,6 +89,7 @@ def rtn_quantize(w: torch.Tensor, quant_type, strategy, group_size=-1, is_symmet
       layout "packed_flat"  codes uint8 (ceil(K*N/2),) — the INT4/UINT4 initializer bytes;
       layout "matmul_nbits" codes uint8 (N, G, gs*bits/8), scale f32 (N, G), zp uint8
                             (N, ceil(G/2)) [4-bit, G>1] or (N, G).
+    ``out`` = pre-allocated ``(codes, scale, zp)`` CUDA tensors of ``output_shapes(...)``.
     """
     lib = _lib.load()
     k, n = _check_weight(w)
@@ -84,7 +98,14 @@ def rtn_quantize(w: torch.Tensor, quant_type, strategy, group_size=-1, is_symmet
     rows = num_rows(k, n, st, group_size)
     bits = 4 if qt in (0, 1) else 8
     device = w.device
-    if layout == "kn":
+    if out is not None:
+        codes, scale, zp = out
+        want = output_shapes(k, n, quant_type, strategy, group_size, layout)
+        if (tuple(codes.shape), tuple(scale.shape), tuple(zp.shape)) != tuple(tuple(s) for s in want) or not (
+                codes.is_contiguous() and scale.is_contiguous() and zp.is_contiguous()
+                and codes.dtype == torch.uint8 and scale.dtype == torch.float32 and zp.dtype == torch.uint8):
+            raise ValueError("out tensors do not match output_shapes()")
+    elif layout == "kn":
         codes = torch.empty((k, n), dtype=torch.uint8, device=device)
         zp = torch.empty((rows,), dtype=torch.uint8, device=device)
         scale = torch.empty((rows,), dtype=torch.float32, device=device)
