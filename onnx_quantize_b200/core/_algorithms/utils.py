@@ -46,7 +46,7 @@ def _post_process_array(preprocessed_array, original_array, strategy, group_size
 # ------------------------------------------------------------------------------------------------
 def _codes_to_numpy(codes_t: torch.Tensor, quant_type: QuantType) -> np.ndarray:
     """uint8 device bytes → host array in the reference's dtype (zero-copy reinterpretation)."""
-    return codes_t.cpu().numpy().view(quant_type.np_dtype)
+    return dev.to_numpy(codes_t).view(quant_type.np_dtype)
 
 
 def _zp_to_numpy(zp_t: torch.Tensor, quant_type: QuantType, zp_dtype) -> np.ndarray:
@@ -211,10 +211,10 @@ def _dequantize_array(q_array, scale, zero_point, *, preprocess=False, strategy=
         z = _zp_to_device_bytes(zero_point, quant_type, rows)
     out = D.dequantize(codes.contiguous(), s, z, quant_type, st, gs)
     if preprocess:
-        return out.cpu().numpy()
+        return dev.to_numpy(out)
     if st == "channel":
         out = out.t()
-    return out.cpu().numpy().reshape(q.shape)
+    return dev.to_numpy(out).reshape(q.shape)
 
 
 def _fake_quantize_array(array, scale, zero_point, quant_type, is_symmetric, reduce_range):

@@ -87,8 +87,8 @@ def _prepare_for_matmul_nbits(w_q: np.ndarray, w_scale: np.ndarray, w_zero_point
     b, zp = D.pack_matmul_nbits(codes, zp_bytes, gs, bits)
     scales = w_scale.reshape(-1, g)
     if float_zp:   # HQQ keeps float zero points un-packed (not on this package's hot path)
-        return b.cpu().numpy(), scales, np.reshape(z, (n, -1)).astype(qconfig.weights.zp_dtype)
-    return b.cpu().numpy(), scales, zp.cpu().numpy()
+        return dev.to_numpy(b), scales, np.reshape(z, (n, -1)).astype(qconfig.weights.zp_dtype)
+    return dev.to_numpy(b), scales, zp.cpu().numpy()
 
 
 def quantize_weights(op, w, qconfig: QConfig, out=None, is_matmul_nbits_compatible: bool = False):

@@ -272,3 +272,23 @@ def test_minmax_golden_and_ragged_sizes(cuda, golden):
         o.collect("y", b)
     assert np.array_equal(bits(c.compute_range("y")[0]), bits(o.compute_range("y")[0]))
     assert np.array_equal(bits(c.compute_range("y")[1]), bits(o.compute_range("y")[1]))
+
+
+def test_large_pageable_arrays_take_the_staged_copies(cuda):
+    """>= 8 MB inputs go up through the pinned staging chunks (several chunks, ragged tail) and the
+    codes come back through pinned memory: results identical to the oracle, arrays writable."""
+    import onnx_quantize_b200 as q
+    from onnx_quantize_b200 import _device as dev
+    from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(21)
+    w = (rng.standard_normal((4224, 4100)) * 0.02).astype(np.float32)        # 69 MB: three staging chunks
+    up = dev.to_device_f32(w)
+    assert torch.equal(up.cpu(), torch.from_numpy(w))
+    assert torch.equal(dev.to_device_f32(w[::2]).cpu(), torch.from_numpy(np.ascontiguousarray(w[::2])))   # strided view
+    codes, s, z = _rtn_quantize(w, q.QuantType.QUInt4, q.QuantizationStrategy.GROUP, 128, False, False, 0.9, False,
+                                np.dtype(np.float32), q.QuantType.QUInt4.np_dtype)
+    qo, so, zo = O.rtn_quantize(w, "uint4", "group", 128, False, False, 0.9, False)
+    assert np.array_equal(codes.astype(np.uint8), qo.astype(np.uint8))
+    assert np.array_equal(s.view(np.uint32), so.view(np.uint32)) and np.array_equal(z.astype(np.uint8), zo.astype(np.uint8))
+    assert codes.flags.writeable and codes.shape == w.shape
