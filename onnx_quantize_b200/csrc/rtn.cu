@@ -157,13 +157,24 @@ static void launch_fused(const FusedArgs& a, int mode, cudaStream_t st) {
 }
 
 // the HBM-bound route: no search, uint4 codes in the MatMulNBits layout (rtn_stream.cuh)
+template <int GS>
+static void launch_stream_single(const FusedArgs& a, dim3 grid, cudaStream_t st) {
+  static bool opted_in = false;   // > 48 KB of dynamic shared memory for GS = 128
+  if (!opted_in) {
+    cudaFuncSetAttribute(rtn_group_nbits4_kernel<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         stream_dyn_bytes<GS>());
+    opted_in = true;
+  }
+  rtn_group_nbits4_kernel<GS><<<grid, kStreamThreads, stream_dyn_bytes<GS>(), st>>>(a);
+}
+
 static void launch_stream_gs(const FusedArgs& a, int64_t gs, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(a.N, kStreamCols), (unsigned)ceil_div(a.G, 2));
   switch (gs) {
-    case 16: rtn_group_nbits4_kernel<16><<<grid, kStreamThreads, 0, st>>>(a); break;
-    case 32: rtn_group_nbits4_kernel<32><<<grid, kStreamThreads, 0, st>>>(a); break;
-    case 64: rtn_group_nbits4_kernel<64><<<grid, kStreamThreads, 0, st>>>(a); break;
-    default: rtn_group_nbits4_kernel<128><<<grid, kStreamThreads, 0, st>>>(a); break;
+    case 16: launch_stream_single<16>(a, grid, st); break;
+    case 32: launch_stream_single<32>(a, grid, st); break;
+    case 64: launch_stream_single<64>(a, grid, st); break;
+    default: launch_stream_single<128>(a, grid, st); break;
   }
 }
 
