@@ -639,10 +639,11 @@ def run_gpu_arm(args):
                    "host_cores_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     "traffic": {"per_launch_bytes": 243.74e6, "algorithmic_bytes_same_launch": 266.3e6 * 4.0 / 4.535,
-                                 "note": "dram__bytes_read+write of one 4096x14336 launch (ncu --set full, "
-                                         "profiles/r1_prof_rtn_details.txt): 235.2 MB read = the f32 weight once, "
-                                         "8.5 MB written (the rest of the 29 MB result is still in L2 at kernel end)"},
+                     "traffic": 243.74e6,
+                     "traffic_note": "dram__bytes_read+write of ONE 4096x14336 launch of the kernel (ncu --set full, "
+                                     "profiles/r1_prof_rtn_final_details.txt): 235.2 MB read = the f32 weight once, "
+                                     "8.5 MB written (the rest of the 29 MB result is still in L2 at kernel end); "
+                                     "algorithmic bytes of that launch: 266.3 MB",
                      "peak_source": peak_src,
                      "kernel": "rtn_group_mse4_kernel<128>",
                      "compute_pipes_ncu": {"xu_mufu_busy_pct": 73, "issue_active_pct": 52,
@@ -661,8 +662,9 @@ def run_gpu_arm(args):
             "ms_per_step": ms_plain, "value": world * in_bytes / (ms_plain * 1e-3) / 1e9, "unit": "GB/s",
             "roofline": {"bound": "hbm", "kernel": "rtn_group_nbits4_kernel<128>", "achieved": achieved_plain,
                          "peak": peak, "unit": "GB/s", "frac": achieved_plain / peak,
-                         "traffic": {"per_launch_bytes": 244.14e6,
-                                     "note": "one 4096x14336 launch, profiles/r1_stream_v2_raw.csv"}}}},
+                         "traffic": 244.14e6,
+                         "traffic_note": "dram bytes of one 4096x14336 launch (profiles/r1_stream_v2_raw.csv); "
+                                         "algorithmic bytes of that launch: 266.3 MB"}}},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_mse * 1e3,
         "clocks": sampler.summary() if sampler else None,
