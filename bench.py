@@ -74,44 +74,56 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def _cpu_slice(args):
-    w, mse = args
+_CPU_WEIGHTS: list = []          # filled BEFORE the worker processes are forked: inherited, never pickled
+
+
+def _cpu_slice(task):
+    j, c0, c1, mse = task
     from oracle import np_oracle as O
+    w = np.ascontiguousarray(_CPU_WEIGHTS[j][:, c0:c1])
     q, s, z = O.rtn_quantize(w, "uint4", "group", 128, False, False, 0.9, mse)
     b, bs, bz = O.matmul_nbits_layout(q, s, z, 128, 4)
     return b.shape
 
 
-def cpu_reference_step(w: np.ndarray, mse: bool, pool, cores: int) -> float:
-    """One bounded-sample step on the host: quantize `w` with the oracle, split over column
-    slices (groups never span columns, so the result is identical)."""
-    n = w.shape[1]
-    step = -(-n // cores)
-    step += (-step) % 2
-    chunks = [np.ascontiguousarray(w[:, i:i + step]) for i in range(0, n, step)]
+def cpu_reference_step(mse: bool, pool, cols_per_task: int = 256) -> float:
+    """One bounded-sample step on the host: every matrix of the sample quantized with the oracle,
+    split over column slices (groups never span columns, so the result is identical), largest
+    slices first."""
+    tasks = [(j, c, min(c + cols_per_task, w.shape[1]), mse) for j, w in enumerate(_CPU_WEIGHTS)
+             for c in range(0, w.shape[1], cols_per_task)]
+    tasks.sort(key=lambda t: -_CPU_WEIGHTS[t[0]].shape[0] * (t[2] - t[1]))
     t0 = time.perf_counter()
     if pool is None:
-        for c in chunks:
-            _cpu_slice((c, mse))
+        for t in tasks:
+            _cpu_slice(t)
     else:
-        list(pool.map(_cpu_slice, [(c, mse) for c in chunks]))
+        list(pool.map(_cpu_slice, tasks, chunksize=1))
     return time.perf_counter() - t0
 
 
-def run_cpu_arm(args, sample_shape=(4096, 4096)):
+def run_cpu_arm(args, sample=None):
+    """The reference's path on the host cores: the oracle port over one Llama-3-8B-shaped layer
+    (7 matrices, 218 M elements = 1/32 of the workload) per step, all cores."""
+    import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(0)
-    w = (rng.standard_normal(sample_shape) * 0.02).astype(np.float32)
-    with ProcessPoolExecutor(max_workers=cores) as pool:
-        for _ in range(max(args.warmup, 0) and 1):
-            cpu_reference_step(w, True, pool, cores)
-        times = [cpu_reference_step(w, True, pool, cores) for _ in range(max(args.steps, 1))]
+    shapes = sample or [(k, n) for _, k, n in LLAMA3_8B_LAYER]
+    _CPU_WEIGHTS.clear()
+    _CPU_WEIGHTS.extend((rng.standard_normal(shp, dtype=np.float32) * np.float32(0.02)) for shp in shapes)
+    nbytes = sum(w.nbytes for w in _CPU_WEIGHTS)
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork")) as pool:
+        list(pool.map(_cpu_slice, [(0, 0, 2, False)] * cores))          # start the workers (imports) untimed
+        for _ in range(1 if args.warmup > 0 else 0):
+            cpu_reference_step(True, pool)
+        times = [cpu_reference_step(True, pool) for _ in range(max(args.steps, 1))]
     t = statistics.mean(times)
-    gbs = w.nbytes / t / 1e9
-    sample = f"one {sample_shape[0]}x{sample_shape[1]} float32 weight (q_proj-shaped) per step, " \
-             f"column slices over {cores} processes"
-    return gbs, t, cores, sample
+    gbs = nbytes / t / 1e9
+    sample_txt = f"one Llama-3-8B-shaped layer per step ({len(shapes)} matrices, {nbytes / 4 / 1e6:.0f} M elements = " \
+                 f"1/{N_LAYERS} of the workload), 256-column slices over {cores} forked processes"
+    _CPU_WEIGHTS.clear()
+    return gbs, t, cores, sample_txt
 
 
 # ------------------------------------------------------------------------------------------------
