@@ -142,3 +142,26 @@ def test_plugin_registry_round_trip():
     assert _ALGORITHM_REGISTRY.pop("mine") is Mine
     with pytest.raises(TypeError, match="must declare an 'algorithm_type' field"):
         q.register_algorithm_config(type("Bad", (q.AlgorithmConfig,), {}))
+
+
+def test_output_shapes_match_the_oracle_layouts():
+    """device_api.output_shapes (pure host logic; sizes the staging buffers of the bulk pipeline)
+    against the arrays the oracle produces for the same configuration."""
+    from onnx_quantize_b200 import device_api as D
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(0)
+    for k, n, qt, st, gs in ((256, 48, "uint4", "group", 128), (128, 36, "uint4", "group", 32),
+                             (64, 20, "int8", "channel", -1), (96, 8, "int4", "tensor", -1),
+                             (128, 16, "uint8", "group", 64), (128, 12, "uint4", "group", -1)):
+        w = rng.standard_normal((k, n)).astype(np.float32)
+        q, s, z = O.rtn_quantize(w, qt, st, gs)
+        shp = D.output_shapes(k, n, qt, st, gs, "kn")
+        assert tuple(shp[0]) == q.shape and int(np.prod(shp[1])) == np.size(s) == int(np.prod(shp[2]))
+        flat = D.output_shapes(k, n, qt, st, gs, "packed_flat")
+        assert flat[0] == ((k * n + 1) // 2,)
+        if st == "group" and qt in ("uint4", "uint8"):
+            bits = 4 if qt == "uint4" else 8
+            g = gs if gs > 0 else k
+            b, bs, bz = O.matmul_nbits_layout(q, s, z, g, bits)
+            m = D.output_shapes(k, n, qt, st, gs, "matmul_nbits")
+            assert tuple(m[0]) == b.shape and tuple(m[1]) == bs.shape and tuple(m[2]) == np.reshape(bz, (n, -1)).shape
