@@ -325,7 +325,13 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
   } else if (strategy == B200Q_TENSOR && !mse && layout == B200Q_KN_BYTES && (K * N) % 4 == 0 &&
              ((uintptr_t)W % 16 == 0) && ((uintptr_t)out_codes % 4 == 0)) {
     // streamlined per-tensor route: min/max partials, fold + parameters, vectorised codes
-    const int gsz = minmax_grid(K * N);
+    // grid sizes from a sweep on two 4096 x 4096 weights (tools/sweep_cfg1.sh): 2 CTAs/SM for the
+    // min/max pass leave room for the next weight's pass to overlap the code pass (4 CTAs/SM)
+    int gsz = minmax_grid(K * N);
+    if (gsz > kNumSMs * 2) gsz = kNumSMs * 2;
+    int fsz = kNumSMs * 4;
+    if (const char* e = getenv("B200Q_TENSOR_P_CTAS")) { const int v = atoi(e); if (v > 0 && kNumSMs * v < gsz) gsz = kNumSMs * v; }
+    if (const char* e = getenv("B200Q_TENSOR_F_CTAS")) { const int v = atoi(e); if (v > 0) fsz = kNumSMs * v; }
     // weights up to 96 MB stay in L2 between the two passes (evict_last on the first read)
     // Both launches are programmatic (PDL): the code pass is resident and waiting when the min/max
     // pass retires, and — under b200q_assume_inputs_resident — the min/max pass of the NEXT weight
@@ -334,7 +340,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     launch_minmax_partials(W, K * N, ws.partials, nullptr, K * N * 4 <= (96ll << 20) ? 1 : 0, inputs_resident(),
                            gsz, st);
     B200Q_LAUNCH_OK();
-    launch_pdl(quantize_flat_kernel, dim3(kNumSMs * 4), dim3(256), st, true,   // one wave: 4 CTAs/SM
+    launch_pdl(quantize_flat_kernel, dim3(fsz), dim3(256), st, true,
                W, K * N / 4, qs, (const float*)nullptr,
                (const unsigned char*)nullptr, (unsigned int*)out_codes, (const float2*)ws.partials, gsz, clip,
                out_scale, zp_rows, ws.enc_min, ws.enc_max);
