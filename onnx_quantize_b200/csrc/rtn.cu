@@ -70,10 +70,11 @@ struct RtnWorkspace {
   float2* partials;
   float* err;
   unsigned char* codes_tmp;
+  float* tensor_sums;      // TENSOR + MSE: [20][2][n_blocks] block sums of the parallel pairwise summation
   size_t total;
 };
 
-static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool mse) {
+static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool mse, bool tensor = false) {
   RtnWorkspace w;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -89,6 +90,7 @@ static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool m
   w.partials = (float2*)take((size_t)kMinMaxMaxBlocks * sizeof(float2));
   w.err = (float*)take(mse ? (size_t)rows * kMseCandidates * 4 : 0);
   w.codes_tmp = (unsigned char*)take((size_t)K * N);
+  w.tensor_sums = (float*)take(mse && tensor ? (size_t)kMseCandidates * 2 * tensor_mse_plan(K * N).n_blocks * 4 : 0);
   w.total = off;
   return w;
 }
@@ -198,6 +200,30 @@ static void launch_stream_batch(const StreamBatch& b, cudaStream_t st) {
   rtn_group_nbits4_batch_kernel<GS><<<(unsigned)b.total_tiles, kStreamThreads, 0, st>>>(b);
 }
 
+// err[cand][row] for every parameter row: the exact error sums of the 20 shrink candidates
+static int launch_mse_error_table(const float* W, const RowMap& m, const QSpec& qs, const RtnWorkspace& ws,
+                                  float* err, cudaStream_t st) {
+  if (m.strategy == B200Q_TENSOR && ws.tensor_sums != nullptr) {
+    const TensorPlan plan = tensor_mse_plan(m.K * m.N);
+    if (plan.n_blocks >= 64) {
+      const int lanes = plan.block <= 128 && plan.block % 8 == 0;
+      dim3 grid((unsigned)ceil_div(plan.n_blocks, lanes ? 32 : 256), kMseCandidates);
+      mse_tensor_block_sums_kernel<<<grid, 256, 0, st>>>(W, plan.block, plan.n_blocks, qs, ws.enc_min, ws.enc_max,
+                                                         ws.tensor_sums, lanes);
+      B200Q_LAUNCH_OK();
+      mse_tensor_combine_kernel<<<kMseCandidates, 1024, 0, st>>>(ws.tensor_sums, plan.n_blocks, err);
+      B200Q_LAUNCH_OK();
+      return B200Q_OK;
+    }
+  }
+  const int64_t cols = m.strategy == B200Q_TENSOR ? 1 : m.N;
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)m.G);
+  dim3 block(32, kMseCandidates);
+  mse_error_table_kernel<<<grid, block, 0, st>>>(W, m, qs, ws.enc_min, ws.enc_max, err);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
 int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, int64_t group_size,
                  int symmetric, int reduce_range, double clip_ratio, int mse, float* out_scale,
                  unsigned char* out_zp, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -207,7 +233,7 @@ int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, 
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   rc = launch_rowstats(W, s.map, s.rows, ws, st);
@@ -215,11 +241,7 @@ int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, 
   const int blocks = (int)ceil_div(s.rows, 256);
   if (mse) {
     B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
-    const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
-    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
-    dim3 block(32, kMseCandidates);
-    mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, ws.err);
-    B200Q_LAUNCH_OK();
+    { const int erc = launch_mse_error_table(W, s.map, qs, ws, ws.err, st); if (erc != B200Q_OK) return erc; }
     mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
     B200Q_LAUNCH_OK();
     mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows, qs,
@@ -241,7 +263,7 @@ extern "C" {
 size_t b200q_rtn_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t group_size, int mse) {
   Shape s;
   if (resolve_shape(K, N, strategy, group_size, &s) != B200Q_OK) return 0;
-  return carve(nullptr, s.rows, K, N, mse != 0).total;
+  return carve(nullptr, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR).total;
 }
 
 int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int strategy,
@@ -269,7 +291,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     B200Q_REQUIRE(m.gs >= 16 && (m.gs & (m.gs - 1)) == 0, B200Q_ERR_INVALID_ARG,
                   "MATMUL_NBITS needs a power-of-two group size >= 16 (got %lld)", (long long)m.gs);
   }
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   B200Q_REQUIRE(clip_ratio > 0.0 && clip_ratio <= 1.0, B200Q_ERR_INVALID_ARG,
@@ -350,11 +372,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     rc = launch_rowstats(W, m, s.rows, ws, st);
     if (rc != B200Q_OK) return rc;
     if (mse) {
-      const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
-      dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)m.G);
-      dim3 block(32, kMseCandidates);
-      mse_error_table_kernel<<<grid, block, 0, st>>>(W, m, qs, ws.enc_min, ws.enc_max, ws.err);
-      B200Q_LAUNCH_OK();
+      { const int erc = launch_mse_error_table(W, m, qs, ws, ws.err, st); if (erc != B200Q_OK) return erc; }
       mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
       B200Q_LAUNCH_OK();
       mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows,
@@ -475,16 +493,12 @@ int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int s
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, true);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, true, strategy == B200Q_TENSOR);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   rc = launch_rowstats(W, s.map, s.rows, ws, st);
   if (rc != B200Q_OK) return rc;
-  const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
-  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
-  dim3 block(32, kMseCandidates);
-  mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, out_err);
-  B200Q_LAUNCH_OK();
+  { const int erc = launch_mse_error_table(W, s.map, qs, ws, out_err, st); if (erc != B200Q_OK) return erc; }
   return B200Q_OK;
 }
 
@@ -500,7 +514,7 @@ int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strate
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   rc = launch_rowstats(W, s.map, s.rows, ws, st);
@@ -508,11 +522,7 @@ int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strate
   int blocks = (int)ceil_div(s.rows, 256);
   if (mse) {
     B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
-    const int64_t cols = strategy == B200Q_TENSOR ? 1 : N;
-    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)s.map.G);
-    dim3 block(32, kMseCandidates);
-    mse_error_table_kernel<<<grid, block, 0, st>>>(W, s.map, qs, ws.enc_min, ws.enc_max, ws.err);
-    B200Q_LAUNCH_OK();
+    { const int erc = launch_mse_error_table(W, s.map, qs, ws, ws.err, st); if (erc != B200Q_OK) return erc; }
     mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
     B200Q_LAUNCH_OK();
   }

@@ -237,3 +237,23 @@ def test_no_out_of_bounds_writes_through_the_c_abi(cuda, k, n, gs, mse):
     assert np.array_equal(host[offs[0]:offs[0] + sizes[0]], ob.reshape(-1))
     assert np.array_equal(host[offs[1]:offs[1] + sizes[1]].view(np.float32).view(np.uint32), bits(os_).reshape(-1))
     assert np.array_equal(host[offs[2]:offs[2] + sizes[2]], oz.reshape(-1))
+
+
+@pytest.mark.parametrize("k,n", [(4096, 132), (2048, 96), (1024, 1024), (1000, 52), (520, 512)])
+def test_tensor_mse_parallel_pairwise_matches_oracle(cuda, k, n):
+    """TENSOR + MSE: NumPy's pairwise sum over the flat array evaluated as independent blocks plus
+    a perfect binary combine tree (mse_generic.cuh) — 8-lane leaves (2048 x 96: B = 96), the
+    generic per-block recursion (4096 x 132: B = 264; 520 x 512: B = 130), and the single-thread
+    fallback (1000 x 52: 4 blocks).  Error sums to 4 ulp-of-sum (np.power is host-dependent),
+    outputs identical."""
+    from onnx_quantize_b200 import device_api as D
+    rng = np.random.default_rng(k + n)
+    w = (rng.standard_normal((k, n)) * 0.02).astype(np.float32)
+    wt = torch.from_numpy(w).to(cuda)
+    err = D.mse_error_table(wt, "int8", "tensor", -1, True).cpu().numpy().reshape(-1)
+    lo, hi, trace = O.mse_min_max(O.to_rows(w, "tensor"), "int8", "tensor", True, False, return_trace=True)
+    ref = np.array([float(np.asarray(t).reshape(-1)[0]) for t in trace], np.float32)
+    np.testing.assert_allclose(err[:len(ref)], ref, rtol=3e-7 * 4, atol=0)
+    q, s, z = _product(w, "int8", "tensor", -1, True, False, 1.0, True)
+    qo, so, zo = O.rtn_quantize(w, "int8", "tensor", -1, True, False, 1.0, True)
+    assert np.array_equal(bits(s).reshape(-1), bits(so).reshape(-1)) and np.array_equal(as_i8(q, "int8"), as_i8(qo, "int8"))
