@@ -149,6 +149,69 @@ static __global__ void __launch_bounds__(256) mse_tensor_block_sums_kernel(
   }
 }
 
+// ---- the same for ANY n: when the exact-halving prefix is short (n with few factors of two) the
+// recursion is cut where nodes drop to <= `limit` elements instead.  One thread walks NumPy's split
+// rule once and writes the nodes in order plus the post-order program (0 = push next node sum,
+// 1 = add the two topmost); the nodes are summed in parallel (one thread each, the generic
+// recursion below the cut); one thread per candidate replays the program.
+constexpr int kPwMaxNodes = 65536;
+struct PwNode { int64_t off, n; };
+
+static __global__ void pw_plan_kernel(int64_t n, int64_t limit, PwNode* __restrict__ nodes,
+                                      unsigned char* __restrict__ ops, int* __restrict__ counts) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  struct Frame { int64_t off, n; int visited; };
+  Frame st[64];
+  int sp = 0, n_nodes = 0, n_ops = 0;
+  st[sp++] = Frame{0, n, 0};
+  while (sp > 0) {
+    Frame& top = st[sp - 1];
+    if (top.n <= limit) {
+      nodes[n_nodes++] = PwNode{top.off, top.n};
+      ops[n_ops++] = 0;
+      --sp;
+      continue;
+    }
+    int64_t n2 = top.n / 2;
+    n2 -= n2 % 8;
+    if (top.visited == 0) { top.visited = 1; st[sp++] = Frame{top.off, n2, 0}; }
+    else if (top.visited == 1) { top.visited = 2; st[sp++] = Frame{top.off + n2, top.n - n2, 0}; }
+    else { ops[n_ops++] = 1; --sp; }
+  }
+  counts[0] = n_nodes;
+  counts[1] = n_ops;
+}
+
+// sums: [20][kPwMaxNodes]
+static __global__ void __launch_bounds__(128) pw_node_sums_kernel(
+    const float* __restrict__ W, const PwNode* __restrict__ nodes, const int* __restrict__ counts, QSpec qs,
+    const unsigned int* __restrict__ enc_min, const unsigned int* __restrict__ enc_max, float* __restrict__ sums) {
+  const int cand = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= counts[0]) return;
+  const float lo0 = fminf(ordered_to_float(enc_min[0]), 0.0f);
+  const float hi0 = fmaxf(ordered_to_float(enc_max[0]), 0.0f);
+  const float p = kShrink[cand];
+  const QParam qp = qparam_from_range(__fmul_rn(p, lo0), __fmul_rn(p, hi0), qs);
+  ErrFn f;
+  f.scale = qp.scale; f.zp = qp.zp; f.qmin = qs.qmin; f.qmax = qs.qmax; f.w = W; f.stride = 1;
+  sums[(int64_t)cand * kPwMaxNodes + i] = pairwise_sum(f, nodes[i].off, nodes[i].n);
+}
+
+static __global__ void pw_replay_kernel(const float* __restrict__ sums, const unsigned char* __restrict__ ops,
+                                        const int* __restrict__ counts, float* __restrict__ err) {
+  const int cand = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cand >= kMseCandidates) return;
+  float st[64];
+  int sp = 0, next = 0;
+  const int n_ops = counts[1];
+  for (int k = 0; k < n_ops; ++k) {
+    if (ops[k] == 0) st[sp++] = sums[(int64_t)cand * kPwMaxNodes + next++];
+    else { const float r = st[--sp]; st[sp - 1] = __fadd_rn(st[sp - 1], r); }
+  }
+  err[cand] = st[0];
+}
+
 // one CTA per candidate: v[i] <- v[2i] + v[2i+1], level by level, ping-pong between the two halves of
 // `work` ([20][2][n_blocks]); err[cand] = the root
 static __global__ void __launch_bounds__(1024) mse_tensor_combine_kernel(float* __restrict__ work, int64_t n_blocks,

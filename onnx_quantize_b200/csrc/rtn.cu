@@ -90,7 +90,14 @@ static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool m
   w.partials = (float2*)take((size_t)kMinMaxMaxBlocks * sizeof(float2));
   w.err = (float*)take(mse ? (size_t)rows * kMseCandidates * 4 : 0);
   w.codes_tmp = (unsigned char*)take((size_t)K * N);
-  w.tensor_sums = (float*)take(mse && tensor ? (size_t)kMseCandidates * 2 * tensor_mse_plan(K * N).n_blocks * 4 : 0);
+  {
+    // perfect-tree plan: [20][2][n_blocks] floats; general plan: [20][kPwMaxNodes] sums, the node table,
+    // the post-order program (2 * nodes) and two counters — whichever is larger
+    const size_t perfect = (size_t)kMseCandidates * 2 * tensor_mse_plan(K * N).n_blocks * 4;
+    const size_t general = (size_t)kMseCandidates * kPwMaxNodes * 4 + (size_t)kPwMaxNodes * sizeof(PwNode) +
+                           (size_t)2 * kPwMaxNodes + 256;
+    w.tensor_sums = (float*)take(mse && tensor ? (perfect > general ? perfect : general) : 0);
+  }
   w.total = off;
   return w;
 }
@@ -212,6 +219,23 @@ static int launch_mse_error_table(const float* W, const RowMap& m, const QSpec& 
                                                          ws.tensor_sums, lanes);
       B200Q_LAUNCH_OK();
       mse_tensor_combine_kernel<<<kMseCandidates, 1024, 0, st>>>(ws.tensor_sums, plan.n_blocks, err);
+      B200Q_LAUNCH_OK();
+      return B200Q_OK;
+    }
+    const int64_t n = m.K * m.N;
+    if (n >= 32768) {   // few factors of two: cut NumPy's recursion at <= limit elements per node
+      int64_t limit = ceil_div(n, kPwMaxNodes / 4);   // nodes end up between limit/2 - 8 and limit: <= ~32768 of them
+      if (limit < 128) limit = 128;
+      float* sums = ws.tensor_sums;
+      PwNode* nodes = (PwNode*)(sums + (size_t)kMseCandidates * kPwMaxNodes);
+      unsigned char* ops = (unsigned char*)(nodes + kPwMaxNodes);
+      int* counts = (int*)(ops + 2 * kPwMaxNodes);
+      pw_plan_kernel<<<1, 32, 0, st>>>(n, limit, nodes, ops, counts);
+      B200Q_LAUNCH_OK();
+      dim3 grid((unsigned)(kPwMaxNodes / 128), kMseCandidates);
+      pw_node_sums_kernel<<<grid, 128, 0, st>>>(W, nodes, counts, qs, ws.enc_min, ws.enc_max, sums);
+      B200Q_LAUNCH_OK();
+      pw_replay_kernel<<<1, 32, 0, st>>>(sums, ops, counts, err);
       B200Q_LAUNCH_OK();
       return B200Q_OK;
     }

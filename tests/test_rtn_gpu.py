@@ -239,12 +239,13 @@ def test_no_out_of_bounds_writes_through_the_c_abi(cuda, k, n, gs, mse):
     assert np.array_equal(host[offs[2]:offs[2] + sizes[2]], oz.reshape(-1))
 
 
-@pytest.mark.parametrize("k,n", [(4096, 132), (2048, 96), (1024, 1024), (1000, 52), (520, 512)])
+@pytest.mark.parametrize("k,n", [(4096, 132), (2048, 96), (1024, 1024), (1000, 52), (520, 512), (2049, 515), (96, 40)])
 def test_tensor_mse_parallel_pairwise_matches_oracle(cuda, k, n):
     """TENSOR + MSE: NumPy's pairwise sum over the flat array evaluated as independent blocks plus
     a perfect binary combine tree (mse_generic.cuh) — 8-lane leaves (2048 x 96: B = 96), the
-    generic per-block recursion (4096 x 132: B = 264; 520 x 512: B = 130), and the single-thread
-    fallback (1000 x 52: 4 blocks).  Error sums to 4 ulp-of-sum (np.power is host-dependent),
+    generic per-block recursion (4096 x 132: B = 264; 520 x 512: B = 130), the general cut of the
+    recursion for sizes with few factors of two (1000 x 52, 2049 x 515: an odd element count) and
+    the single-thread walk for small tensors (96 x 40).  Error sums to 4 ulp-of-sum (np.power is host-dependent),
     outputs identical."""
     from onnx_quantize_b200 import device_api as D
     rng = np.random.default_rng(k + n)
