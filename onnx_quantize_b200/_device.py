@@ -78,9 +78,10 @@ def _staging(dev: torch.device):
     return st
 
 
-def _upload_pageable(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
-    """Contiguous pageable float32 CPU tensor → CUDA tensor on the current stream."""
-    out = torch.empty(t.shape, dtype=torch.float32, device=dev)
+def _upload_pageable(t: torch.Tensor, dev: torch.device, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Contiguous pageable float32 CPU tensor → CUDA tensor (``out`` or a new one) on the current stream."""
+    if out is None:
+        out = torch.empty(t.shape, dtype=torch.float32, device=dev)
     src = t.reshape(-1).numpy()
     dst = out.view(-1)
     total = src.shape[0]
@@ -97,6 +98,15 @@ def _upload_pageable(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
             dst[off:off + m].copy_(bufs[b][:m], non_blocking=True)
             evs[b].record()
     return out
+
+
+def upload_into(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """``dst.copy_(src)`` for a float32 CPU tensor on the current stream: asynchronous DMA for pinned
+    sources, the staged multi-threaded path for large pageable ones."""
+    if src.is_pinned() or not src.is_contiguous() or src.numel() * 4 < _STAGE_MIN_BYTES:
+        dst.copy_(src, non_blocking=True)
+    else:
+        _upload_pageable(src, dst.device, dst)
 
 
 def to_numpy(t: torch.Tensor) -> np.ndarray:

@@ -155,7 +155,7 @@ def _bulk_locked(weights, spec: RtnSpec, keep_on_device: bool, device, slots):
         with torch.cuda.stream(h2d):
             h2d.wait_event(slot.consumed)
             wd = slot.weight(k, n)
-            wd.copy_(src, non_blocking=True)
+            dev.upload_into(src, wd)          # pinned: plain DMA; pageable model weights: staged, multi-threaded
             slot.ready.record(h2d)
         compute.wait_event(slot.ready)
         if keep_on_device:

@@ -292,3 +292,20 @@ def test_large_pageable_arrays_take_the_staged_copies(cuda):
     assert np.array_equal(codes.astype(np.uint8), qo.astype(np.uint8))
     assert np.array_equal(s.view(np.uint32), so.view(np.uint32)) and np.array_equal(z.astype(np.uint8), zo.astype(np.uint8))
     assert codes.flags.writeable and codes.shape == w.shape
+
+
+def test_bulk_pipeline_with_pageable_weights(cuda):
+    """quantize_weights_bulk on ordinary NumPy arrays (what an ONNX model's initializers are): the
+    staged upload feeds the device slots; results equal the per-weight reference-facing call."""
+    import onnx_quantize_b200 as q
+    from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
+    from onnx_quantize_b200.pipeline import RtnSpec, quantize_weights_bulk
+    rng = np.random.default_rng(5)
+    ws = [(rng.standard_normal(s) * 0.02).astype(np.float32) for s in ((2304, 1024), (256, 64), (1024, 2304), (128, 48))]
+    spec = RtnSpec(q.QuantType.QUInt4, "group", 128, False, False, 0.9, True, "kn")
+    got = quantize_weights_bulk(ws, spec)
+    for w, (c, s, z) in zip(ws, got):
+        qc, qs_, qz = _rtn_quantize(w, q.QuantType.QUInt4, q.QuantizationStrategy.GROUP, 128, False, False, 0.9, True,
+                                    np.dtype(np.float32), q.QuantType.QUInt4.np_dtype)
+        assert np.array_equal(c.reshape(w.shape), qc.astype(np.uint8))
+        assert np.array_equal(s.reshape(-1).view(np.uint32), qs_.reshape(-1).view(np.uint32))
