@@ -674,9 +674,11 @@ def run_gpu_arm(args):
             "ms_per_step": ms_plain, "value": world * in_bytes / (ms_plain * 1e-3) / 1e9, "unit": "GB/s",
             "roofline": {"bound": "hbm", "kernel": "rtn_group_nbits4_kernel<128>", "achieved": achieved_plain,
                          "peak": peak, "unit": "GB/s", "frac": achieved_plain / peak,
-                         "traffic": 244.14e6,
-                         "traffic_note": "dram bytes of one 4096x14336 launch (profiles/r1_stream_v2_raw.csv); "
-                                         "algorithmic bytes of that launch: 266.3 MB"}}},
+                         "traffic": 31.662e9,
+                         "traffic_note": "dram__bytes_read (27.954 GB = the f32 weights once) + dram__bytes_write "
+                                         "(3.708 GB = the packed results once) of the one batched launch over the "
+                                         "whole set, profiles/r1c_batch_stream_full_set.csv; algorithmic bytes of "
+                                         "that launch: 31.65 GB"}}},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_mse * 1e3,
         "clocks": sampler.summary() if sampler else None,
