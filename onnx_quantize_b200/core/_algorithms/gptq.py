@@ -17,6 +17,7 @@ from onnx_quantize_b200.core._dtypes import QuantType
 from onnx_quantize_b200.core._qconfig import (
     AlgorithmConfig,
     QuantizationStrategy,
+    coerce_strategy,
     register_algorithm_config,
 )
 
@@ -50,11 +51,6 @@ class GPTQConfig(AlgorithmConfig):
         assert out is not None, "Output value is required for GPTQ quantization."
         node = out.producer()
         assert "input" in node.meta, "GPTQ requires calibration data in node meta."
-        from onnx_quantize_b200.parallel import prequantized
-
-        cached = prequantized.lookup(w)
-        if cached is not None:
-            return cached
         wa = qconfig.weights
         return _gptq_quantize(w.const_value.numpy(), node.meta["input"], quant_type=wa.dtype,
                               strategy=wa.strategy, is_symmetric=wa.symmetric,
@@ -102,7 +98,8 @@ def _gptq(W, H, quant_type, strategy, group_size, is_symmetric, reduce_range, cl
     """
     from onnx_quantize_b200 import gptq_device as G
 
-    assert isinstance(strategy, QuantizationStrategy)
+    strategy = coerce_strategy(strategy)
+    quant_type = QuantType.coerce(quant_type)
     w = dev.to_device_f32(W)
     h = dev.to_device_f32(H)
     if w.dim() != 2 or h.shape != (w.shape[0], w.shape[0]):

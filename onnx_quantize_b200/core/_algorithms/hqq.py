@@ -100,6 +100,7 @@ def _hqq_quantize(w_f: np.ndarray, quant_type: QuantType, group_size: int, reduc
                   ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """(K,N) float32 weight → ``(codes (K,N) uint4, scale (N*G,1), zero_point (N*G,1) float)``."""
     assert zp_dtype == scale_dtype            # hqq.py:178
+    quant_type = QuantType.coerce(quant_type)
     if quant_type != QuantType.QUInt4:
         raise ValueError(f"HQQ only supports uint4 weight type. Found: {quant_type}")
     w = dev.to_device_f32(w_f)

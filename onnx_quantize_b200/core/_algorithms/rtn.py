@@ -16,6 +16,7 @@ from onnx_quantize_b200.core._dtypes import QuantType
 from onnx_quantize_b200.core._qconfig import (
     AlgorithmConfig,
     QuantizationStrategy,
+    coerce_strategy,
     register_algorithm_config,
 )
 
@@ -35,10 +36,10 @@ class RTNConfig(AlgorithmConfig):
                          ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         from onnx_quantize_b200.parallel import prequantized
 
-        cached = prequantized.lookup(w)
+        wa = qconfig.weights
+        cached = prequantized.lookup(w, wa, self.algorithm_type)
         if cached is not None:   # filled by the multi-GPU pre-pass (SURVEY.md §8b "Threading")
             return cached
-        wa = qconfig.weights
         return _rtn_quantize(w.const_value.numpy(), wa.dtype, strategy=wa.strategy,
                              group_size=wa.group_size, is_symmetric=wa.symmetric,
                              reduce_range=wa.reduce_range, clip_ratio=wa.clip_ratio, mse=wa.mse,
@@ -64,16 +65,38 @@ def _rtn_quantize(array: np.ndarray, quant_type: QuantType, strategy: Quantizati
     dtypes and shapes are the reference's: codes in ``quant_type.np_dtype`` (ml_dtypes int4/uint4
     are one byte per element), scale float32, zero point ``zp_dtype``.
     """
-    assert isinstance(strategy, QuantizationStrategy)
+    strategy = coerce_strategy(strategy)
+    quant_type = QuantType.coerce(quant_type)
     w = dev.to_device_f32(array)
     if w.dim() != 2:
         raise ValueError("weights must be 2-D (in_channels, out_channels)")
     codes, scale, zp = D.rtn_quantize(w, quant_type, strategy, group_size, is_symmetric,
                                       reduce_range, clip_ratio, mse)
-    scale_np = scale.cpu().numpy().astype(scale_dtype, copy=False)
-    zp_np = _zp_to_numpy(zp, quant_type, zp_dtype)
-    scale_np, zp_np = _shape_like_reference(scale_np, zp_np, strategy)
-    return _codes_to_numpy(codes, quant_type), scale_np, zp_np
+    return _finalize_triple(codes, scale, zp, quant_type, strategy, scale_dtype, zp_dtype)
+
+
+def _finalize_triple(codes, scale, zp, quant_type: QuantType, strategy: QuantizationStrategy,
+                     scale_dtype, zp_dtype) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Raw kernel outputs — (K,N) code bytes, flat float32 scales, flat zero-point bytes, as CUDA
+    tensors or host arrays — to what the reference returns (rtn.py:96-109): codes in
+    ``quant_type.np_dtype`` (a reinterpretation of the bytes), scale in ``scale_dtype``, zero point
+    in ``zp_dtype``, parameters shaped 0-d / (N,) / (N*G, 1)."""
+    import torch
+
+    if isinstance(codes, torch.Tensor):
+        codes_np = _codes_to_numpy(codes, quant_type)
+        scale_np = scale.cpu().numpy()
+        zp_np = _zp_to_numpy(zp, quant_type, zp_dtype)
+    else:
+        codes_np = np.asarray(codes).view(quant_type.np_dtype)
+        scale_np = np.asarray(scale)
+        zp_np = np.asarray(zp).view(quant_type.np_dtype)
+        want = np.dtype(zp_dtype) if zp_dtype is not None else quant_type.np_dtype
+        if zp_np.dtype != want:
+            zp_np = zp_np.astype(want)
+    scale_np = scale_np.reshape(-1).astype(scale_dtype, copy=False)
+    scale_np, zp_np = _shape_like_reference(scale_np, zp_np.reshape(-1), strategy)
+    return codes_np, scale_np, zp_np
 
 
 def _quantize_bias(bias, input_scale, weight_scale):

@@ -14,7 +14,7 @@ import torch
 from onnx_quantize_b200 import _device as dev
 from onnx_quantize_b200 import device_api as D
 from onnx_quantize_b200.core._dtypes import QuantType
-from onnx_quantize_b200.core._qconfig import QuantizationStrategy
+from onnx_quantize_b200.core._qconfig import QuantizationStrategy, coerce_strategy
 
 
 # ------------------------------------------------------------------------------------------------
@@ -22,7 +22,7 @@ from onnx_quantize_b200.core._qconfig import QuantizationStrategy
 # ------------------------------------------------------------------------------------------------
 def _preprocess_array(array, strategy, group_size=-1):
     """(K,N) → rows sharing one (scale, zp): tensor → as is, channel → W.T, group → (N*G, gs)."""
-    assert isinstance(strategy, QuantizationStrategy)
+    strategy = coerce_strategy(strategy)
     if strategy == QuantizationStrategy.TENSOR:
         return array
     if strategy == QuantizationStrategy.CHANNEL:
@@ -33,7 +33,7 @@ def _preprocess_array(array, strategy, group_size=-1):
 
 
 def _post_process_array(preprocessed_array, original_array, strategy, group_size=-1):
-    assert isinstance(strategy, QuantizationStrategy)
+    strategy = coerce_strategy(strategy)
     if strategy == QuantizationStrategy.TENSOR:
         return preprocessed_array
     if strategy == QuantizationStrategy.CHANNEL:
@@ -107,7 +107,7 @@ class _RowView:
 # ------------------------------------------------------------------------------------------------
 def _compute_min_max(array, strategy, group_size=-1, clip_ratio=1.0):
     """(min*clip, max*clip) per row with zero included (reference utils.py:42-69)."""
-    assert isinstance(strategy, QuantizationStrategy)
+    strategy = coerce_strategy(strategy)
     view = _RowView(array, strategy)
     lo, hi = D.row_ranges(view.device_weight(), QuantType.QInt8, view.strategy, view.gs,
                           clip_ratio=clip_ratio, mse=False)
@@ -124,6 +124,7 @@ def _compute_min_max_mse(array, quant_type, strategy, group_size, is_symmetric, 
     if (maxshrink, patience, grid, norm) != (0.20, 5, 100.0, 2.4):
         raise NotImplementedError(
             "the device MSE search implements maxshrink=0.20, patience=5, grid=100, norm=2.4")
+    quant_type = QuantType.coerce(quant_type)
     view = _RowView(array, strategy)
     lo, hi = D.row_ranges(view.device_weight(), quant_type, view.strategy, view.gs, is_symmetric,
                           reduce_range, 1.0, mse=True)
@@ -135,6 +136,7 @@ def _compute_min_max_mse(array, quant_type, strategy, group_size, is_symmetric, 
 # ------------------------------------------------------------------------------------------------
 def _compute_qparams(rmin, rmax, quant_type, is_symmetric, reduce_range, scale_dtype, zp_dtype):
     """(scale, zero_point) with the shape of ``rmin`` (reference utils.py:242-299)."""
+    quant_type = QuantType.coerce(quant_type)
     rmin, rmax = np.asarray(rmin), np.asarray(rmax)
     shape = np.broadcast(rmin, rmax).shape
     lo = dev.to_device_f32(np.ascontiguousarray(np.broadcast_to(rmin, shape)).reshape(-1))
@@ -147,6 +149,7 @@ def _compute_qparams(rmin, rmax, quant_type, is_symmetric, reduce_range, scale_d
 def _compute_qparams_from_array(array, quant_type, strategy, group_size, is_symmetric,
                                 reduce_range, clip_ratio, mse, scale_dtype, zp_dtype):
     """Ranges (A2, or A6 when ``mse``) then A3 — reference utils.py:302-348."""
+    quant_type = QuantType.coerce(quant_type)
     view = _RowView(array, strategy)
     _, scale, zp = D.rtn_quantize(view.device_weight(), quant_type, view.strategy, view.gs,
                                   is_symmetric, reduce_range, clip_ratio, mse)
@@ -162,6 +165,7 @@ def _quantize_array_from_qparams(array, scale, zero_point, quant_type, is_symmet
 
     ``scale`` / ``zero_point`` are scalars or one value per row of ``array``.
     """
+    quant_type = QuantType.coerce(quant_type)
     a = np.asarray(array)
     per_row = np.size(scale) > 1
     if a.ndim == 1 and per_row:   # one value per element: a column of single-element rows

@@ -72,6 +72,19 @@ class QuantType(enum.Enum):
                 f"Invalid quantization type '{value}'. Expected one of: {', '.join(_ORDER)}"
             ) from None
 
+    @classmethod
+    def coerce(cls, value) -> "QuantType":
+        """This enum's member for ``value``: a member of this enum, a type name, or the member of the
+        same NAME of another package's ``QuantType`` — the reference's own enum is what arrives when
+        these functions are patched into the reference (``integration.patched_reference``)."""
+        if isinstance(value, cls):
+            return value
+        if isinstance(value, str):
+            return cls.from_string(value)
+        if isinstance(value, enum.Enum) and value.name in cls.__members__:
+            return cls[value.name]
+        raise TypeError(f"not a quantization type: {value!r}")
+
     @property
     def short_name(self) -> str:
         """'int4', 'uint4', 'int8', … — also the key the C ABI wrapper uses."""

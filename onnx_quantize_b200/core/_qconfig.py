@@ -39,6 +39,17 @@ class QuantizationStrategy(str, Enum):
     GROUP = "group"
 
 
+def coerce_strategy(value) -> QuantizationStrategy:
+    """A member of this package's enum for a member of ANY ``QuantizationStrategy`` enum (the
+    reference's own class is what arrives when the array-level functions are patched into the
+    reference).  Plain strings are refused, as the reference's ``isinstance`` assertions do."""
+    if isinstance(value, QuantizationStrategy):
+        return value
+    assert isinstance(value, Enum) and type(value).__name__ == "QuantizationStrategy", \
+        f"strategy must be a QuantizationStrategy, got {value!r}"
+    return QuantizationStrategy(value.value)
+
+
 class QFormat(str, Enum):
     """Graph representation of the quantized model."""
 

@@ -21,9 +21,7 @@ N_MSE_CANDIDATES = 20
 
 
 def _qt(quant_type) -> int:
-    if isinstance(quant_type, str):
-        quant_type = QuantType.from_string(quant_type)
-    name = quant_type.short_name
+    name = QuantType.coerce(quant_type).short_name
     if name not in _lib.QTYPE:
         raise NotImplementedError(f"{quant_type} is not supported on the weight path")
     return _lib.QTYPE[name]

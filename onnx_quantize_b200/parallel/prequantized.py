@@ -1,23 +1,87 @@
-"""Results of a bulk (multi-GPU) pre-quantization pass, keyed by initializer name.
+"""Results of a bulk (multi-GPU) pre-quantization pass, handed to the plugins.
 
 The reference's rewriter calls the plugin one node at a time from a single thread
 (qrules/_common.py:133), so sharding weights over ranks has to happen *before* the rewrite: a
 pre-pass quantizes every target weight (``parallel.shard``), stores the triples here, and the
 registered plugins' ``quantize_weights`` return the stored triple instead of recomputing it.
+
+A stored triple is exactly what the plugin's array-level function would have returned (dtypes and
+shapes of ``_rtn_quantize``: reference rtn.py:96-109), and it is only handed out for the request
+it was computed for: the key is ``(initializer name, digest)`` where the digest covers the
+algorithm tag, every numeric field of ``QWeightArgs`` and a fingerprint of the weight array itself.
+The reference's AWQ / SmoothQuant pre-passes replace an initializer *under the same name*
+(pre_passes/awq.py ``ir.val(node.inputs[1].name, ...)``) and the rewriter rebuilds a per-node
+``QConfig`` (qrules/base.py:57), so a name alone identifies neither the array nor the request.
 """
 from __future__ import annotations
 
-_store: dict[str, tuple] = {}
+import contextlib
+import zlib
+
+import numpy as np
+
+_store: dict[tuple[str, str], tuple] = {}
+_FINGERPRINT_SAMPLES = 1 << 16
 
 
-def put(name: str, triple: tuple) -> None:
-    _store[name] = triple
+def weight_fingerprint(array) -> str:
+    """Shape, dtype and a CRC-32 over a strided sample of ≤ 65 536 elements plus the first and
+    last 4 KiB — cheap next to the quantization of a weight large enough to be worth a pre-pass,
+    and it changes under any rescaling of rows or columns (what AWQ / SmoothQuant do)."""
+    a = np.asarray(array)
+    flat = a.reshape(-1) if a.flags.c_contiguous else np.ascontiguousarray(a).reshape(-1)
+    step = max(1, flat.size // _FINGERPRINT_SAMPLES)
+    crc = zlib.crc32(np.ascontiguousarray(flat[::step]).view(np.uint8))
+    crc = zlib.crc32(flat[:1024].view(np.uint8), crc)
+    crc = zlib.crc32(flat[-1024:].view(np.uint8), crc)
+    return f"{a.shape}|{a.dtype}|{crc:08x}"
 
 
-def lookup(w):
+def request_digest(weight_args, algorithm_tag: str, array) -> str:
+    """Everything the result depends on.  ``weight_args`` is a ``QWeightArgs`` (or any object with
+    the same attributes, e.g. ``pipeline.RtnSpec.as_weight_args()``)."""
+    wa = weight_args
+    strategy = getattr(wa.strategy, "value", wa.strategy)
+    dtype = getattr(wa.dtype, "short_name", wa.dtype)
+    gs = wa.group_size if wa.group_size else -1
+    parts = (algorithm_tag, dtype, strategy, int(gs), bool(wa.symmetric), bool(wa.reduce_range),
+             float(wa.clip_ratio), bool(wa.mse), str(np.dtype(wa.scale_dtype)), str(np.dtype(wa.zp_dtype)),
+             weight_fingerprint(array))
+    return "|".join(str(p) for p in parts)
+
+
+def put(name: str, digest: str, triple: tuple) -> None:
+    _store[(name, digest)] = triple
+
+
+def lookup(w, weight_args, algorithm_tag: str):
+    """The stored triple for initializer ``w`` (an ``ir.Value``: ``.name``, ``.const_value.numpy()``)
+    under this exact request, else None."""
     name = getattr(w, "name", None)
-    return _store.get(name) if name is not None else None
+    if name is None or not _store or not any(k[0] == name for k in _store):
+        return None
+    const = getattr(w, "const_value", None)
+    if const is None:
+        return None
+    return _store.get((name, request_digest(weight_args, algorithm_tag, const.numpy())))
 
 
 def clear() -> None:
     _store.clear()
+
+
+def __len__() -> int:   # pragma: no cover - convenience for debugging
+    return len(_store)
+
+
+@contextlib.contextmanager
+def scope():
+    """Entries published inside the context are dropped at its end, so they cannot leak into a
+    later ``quantize()`` call or another model that reuses initializer names."""
+    before = set(_store)
+    try:
+        yield
+    finally:
+        for key in list(_store):
+            if key not in before:
+                del _store[key]

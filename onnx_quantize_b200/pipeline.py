@@ -4,7 +4,10 @@
 CUDA streams — H2D copy of weight i+1, kernels of weight i and D2H copy of the results of weight
 i-1 overlap — using double-buffered device slots and pinned staging for the results.  It is what
 the multi-GPU pre-pass (``parallel/shard.py``) runs on each rank and what ``bench.py`` times as
-the ``e2e`` figure.  Results are identical to calling ``_rtn_quantize`` per weight.
+the ``e2e`` figure.  The arrays returned are the kernels' own: code BYTES (K,N) uint8, flat float32
+scales and flat zero-point bytes (the values are those of ``_rtn_quantize``; its dtypes and shapes
+are applied by ``core._algorithms.rtn._finalize_triple``, which ``parallel.shard`` does before
+publishing results to the plugins).
 """
 from __future__ import annotations
 
@@ -31,11 +34,25 @@ class RtnSpec:
     clip_ratio: float = 1.0
     mse: bool = False
     layout: str = "kn"
+    scale_dtype: object = np.dtype(np.float32)
+    zp_dtype: object = None            # None: the code dtype (QWeightArgs' default)
 
     @classmethod
     def from_weight_args(cls, wa, layout: str = "kn") -> "RtnSpec":
         return cls(wa.dtype, wa.strategy.value, wa.group_size if wa.group_size else -1,
-                   wa.symmetric, wa.reduce_range, wa.clip_ratio, wa.mse, layout)
+                   wa.symmetric, wa.reduce_range, wa.clip_ratio, wa.mse, layout,
+                   wa.scale_dtype, wa.zp_dtype)
+
+    def as_weight_args(self):
+        """The same request in ``QWeightArgs`` attribute names (what the plugin sees)."""
+        from types import SimpleNamespace
+
+        qt = QuantType.from_string(self.quant_type) if isinstance(self.quant_type, str) else self.quant_type
+        return SimpleNamespace(dtype=qt, strategy=getattr(self.strategy, "value", self.strategy),
+                               group_size=self.group_size, symmetric=self.is_symmetric,
+                               reduce_range=self.reduce_range, clip_ratio=self.clip_ratio, mse=self.mse,
+                               scale_dtype=np.dtype(self.scale_dtype),
+                               zp_dtype=np.dtype(self.zp_dtype) if self.zp_dtype is not None else qt.np_dtype)
 
 
 class _PinnedCarver:

@@ -22,3 +22,10 @@ def golden_keys(npz):
 def parse_rtn_key(key):
     wname, qt, strategy, gs, sym, rr, clip, mse = key.split("|")
     return wname, qt, strategy, int(gs), bool(int(sym)), bool(int(rr)), float(clip), bool(int(mse))
+
+
+def stable_seed(*parts) -> int:
+    """A seed that depends only on the VALUES of ``parts`` (CRC-32 of their repr) — unlike
+    ``hash()``, whose string hashing is salted per process, so a failing case can be replayed."""
+    import zlib
+    return zlib.crc32(repr(parts).encode())

@@ -8,7 +8,7 @@ import pytest
 import onnx_quantize_b200 as q
 from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
 from oracle import np_oracle as O
-from tests.helpers import as_i8, bits
+from tests.helpers import as_i8, bits, stable_seed
 
 pytestmark = pytest.mark.gpu
 QT = {"int4": q.QuantType.QInt4, "uint4": q.QuantType.QUInt4, "int8": q.QuantType.QInt8,
@@ -53,7 +53,7 @@ def test_rtn_random_configurations_bit_exact(cuda, case):
     qt, strategy, k, n, gs, sym, rr, clip, mse, kind = case
     if mse and k * n > 40000:
         mse = False                                   # keep the NumPy oracle's 20 passes quick
-    rng = np.random.default_rng(hash(case) & 0xFFFFFF)
+    rng = np.random.default_rng(stable_seed(case))
     w = _weights(rng, k, n, kind)
     got = _rtn_quantize(w, QT[qt], q.QuantizationStrategy(strategy), gs, sym, rr, clip, mse,
                         np.dtype(np.float32), QT[qt].np_dtype)
@@ -88,7 +88,7 @@ def test_gptq_reference_mode_random_configurations_bit_exact(cuda, case):
     MSE, with dead input channels."""
     from onnx_quantize_b200.core._algorithms.gptq import _gptq
     qt, strategy, k, n, gs, sym, rr, clip, mse, actorder, bs, dead = case
-    rng = np.random.default_rng(hash(case) & 0xFFFFFF)
+    rng = np.random.default_rng(stable_seed(case))
     w = (rng.standard_normal((k, n)) * 0.05).astype(np.float32)
     x = rng.standard_normal((8, 16, k)).astype(np.float32) * rng.uniform(0.5, 2.0, k).astype(np.float32)
     if dead:

@@ -84,18 +84,35 @@ def _worker(rank, world, port, out):
         if rank == 1:
             assert np.abs(hd.numpy() - h_ref).max() / np.abs(h_ref).max() < 1e-6
 
-        # ---- gather of sharded results -------------------------------------------------------
+        # ---- gather of sharded results: packed tensors, point to point, no pickling ------------
         names = [f"w{i}" for i in range(5)]
-        costs = [3, 9, 1, 7, 5]
+        shapes = [(6, 4), (16, 8), (2, 2), (8, 12), (10, 4)]           # (K, N) per unit; codes (K,N) u8, scale/zp (N,)
+        costs = [k * n for k, n in shapes]
         plan = S.assign_units(costs, world)
-        local_res = {names[i]: (np.full(2, i), np.float32(i), np.int8(i)) for i in plan[rank]}
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(local_res, gathered, dst=0)
+        dtypes = (torch.uint8, torch.float32, torch.uint8)
+        layouts, totals = [], []
+        for r in range(world):
+            lay, tot = S.packed_layout([[((shapes[i]), dtypes[0]), ((shapes[i][1],), dtypes[1]),
+                                         ((shapes[i][1],), dtypes[2])] for i in plan[r]])
+            layouts.append(lay)
+            totals.append(tot)
+        local = [(torch.full(shapes[i], i, dtype=torch.uint8), torch.arange(shapes[i][1], dtype=torch.float32) + i,
+                  torch.full((shapes[i][1],), 100 + i, dtype=torch.uint8)) for i in plan[rank]]
+        flat = S.pack_results(local, layouts[rank], totals[rank], torch.device("cpu"))
+        assert all(off % 256 == 0 for unit in layouts[rank] for off, _, _ in unit)
+        bufs = S.gather_packed(flat, totals, dst=0)
         if rank == 0:
-            merged = {}
-            for part in gathered:
-                merged.update(part)
-            assert sorted(merged) == names and all(int(merged[n][1]) == int(n[1:]) for n in names)
+            seen = {}
+            for r, buf in enumerate(bufs):
+                for i, unit in zip(plan[r], S.unpack_results(buf, layouts[r])):
+                    seen[names[i]] = unit
+            assert sorted(seen) == names
+            for i, n in enumerate(names):
+                c, sc, z = seen[n]
+                assert c.shape == shapes[i] and bool((c == i).all()) and bool((z == 100 + i).all())
+                assert torch.equal(sc, torch.arange(shapes[i][1], dtype=torch.float32) + i)
+        else:
+            assert bufs is None
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))

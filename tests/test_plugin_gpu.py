@@ -77,21 +77,102 @@ def test_gptq_plugin_reads_calibration_input_from_node_meta(cuda, rng):
         back.weights.algorithm.quantize_weights(_Value("w1", w), back, out=_Value("y", node=_Node({})))
 
 
-def test_sharded_prepass_publishes_results_for_the_plugins(cuda, rng):
-    """Single-rank run of the multi-GPU pre-pass: every weight is quantized by the bulk pipeline,
-    stored by initializer name, and the plugin returns the stored triple without recomputing."""
+SHARDED_SPECS = [("uint4", "group", 128, False), ("int8", "channel", -1, True), ("int4", "tensor", -1, True),
+                 ("int4", "group", 64, True), ("uint8", "tensor", -1, False)]
+
+
+@pytest.mark.parametrize("dtype,strategy,gs,sym", SHARDED_SPECS)
+def test_sharded_prepass_publishes_results_for_the_plugins(cuda, rng, dtype, strategy, gs, sym):
+    """Single-rank run of the multi-GPU pre-pass: every weight is quantized by the bulk pipeline and
+    stored; the plugin then returns the stored triple, which must be EXACTLY what `_rtn_quantize`
+    returns for the same request — dtype, shape and values, no reinterpretation on the way."""
+    from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
     weights = {f"layer{i}.w": (rng.standard_normal(s) * 0.02).astype(np.float32)
                for i, s in enumerate([(256, 64), (128, 128), (384, 32)])}
-    spec = RtnSpec(q.QuantType.QUInt4, "group", 128, False, False, 1.0, False, "kn")
-    prequantized.clear()
-    try:
+    qt = q.QuantType.from_string(dtype)
+    spec = RtnSpec(qt, strategy, gs, sym, False, 0.9, False, "kn")
+    cfg = q.QConfig(weights=q.QWeightArgs(dtype=dtype, symmetric=sym, clip_ratio=0.9, strategy=strategy,
+                                          group_size=gs if strategy == "group" else (-1 if strategy == "channel" else None)))
+    with prequantized.scope():
         merged = quantize_weights_sharded(weights, spec)
         assert sorted(merged) == sorted(weights)
-        cfg = q.QConfig(weights=q.QWeightArgs(dtype="uint4", group_size=128))
         for name, w in weights.items():
-            triple = cfg.weights.algorithm.quantize_weights(_Value(name, None), cfg)   # no array needed
-            want = O.rtn_quantize(w, "uint4", "group", 128)
-            assert np.array_equal(np.asarray(triple[0]).view(np.uint8), as_i8(want[0], "uint4"))
-            assert np.array_equal(bits(np.asarray(triple[1]).reshape(-1)), bits(want[1].reshape(-1)))
-    finally:
-        prequantized.clear()
+            calls = []
+            value = _Value(name, w)
+            triple = cfg.weights.algorithm.quantize_weights(value, cfg)
+            assert triple is merged[name]                              # served from the store
+            direct = _rtn_quantize(w, qt, cfg.weights.strategy, gs, sym, False, 0.9, False, np.dtype(np.float32),
+                                   cfg.weights.zp_dtype)
+            want = O.rtn_quantize(w, dtype, strategy, gs, sym, False, 0.9, False)
+            for got, ref, orc in zip(triple, direct, want):
+                assert got.dtype == ref.dtype == orc.dtype and got.shape == ref.shape == orc.shape
+                assert np.array_equal(np.asarray(got).astype(np.float32), np.asarray(orc).astype(np.float32))
+            assert np.array_equal(bits(triple[1]), bits(want[1]))
+            if is_matmul_nbits_compatible(cfg, name):              # straight into the reference's packer
+                b, s, z = _prepare_for_matmul_nbits(*triple, cfg)
+                ob, os_, oz = O.matmul_nbits_layout(want[0], want[1], want[2], gs, 4)
+                assert b.dtype == ob.dtype and np.array_equal(b, ob)
+                assert np.array_equal(bits(s), bits(os_)) and np.array_equal(z, oz)
+    assert prequantized.lookup(_Value("layer0.w", weights["layer0.w"]), cfg.weights, "rtn") is None   # scope ended
+
+
+def test_prepass_entries_are_only_served_for_the_request_they_were_computed_for(cuda, rng):
+    """Same initializer name, different array (what AWQ / SmoothQuant leave behind) or different
+    weight arguments → the plugin recomputes; the GPTQ plugin never reads RTN entries."""
+    w = (rng.standard_normal((256, 64)) * 0.02).astype(np.float32)
+    spec = RtnSpec(q.QuantType.QUInt4, "group", 128, False, False, 1.0, False, "kn")
+    cfg = q.QConfig(weights=q.QWeightArgs(dtype="uint4", group_size=128))
+    with prequantized.scope():
+        merged = quantize_weights_sharded({"w": w}, spec)
+        assert cfg.weights.algorithm.quantize_weights(_Value("w", w), cfg) is merged["w"]
+        w2 = w * np.linspace(0.5, 2.0, 256, dtype=np.float32)[:, None]           # rescaled rows, same name
+        got = cfg.weights.algorithm.quantize_weights(_Value("w", w2), cfg)
+        assert got is not merged["w"]
+        want = O.rtn_quantize(w2, "uint4", "group", 128)
+        assert np.array_equal(as_i8(got[0], "uint4"), as_i8(want[0], "uint4"))
+        for other in (q.QWeightArgs(dtype="uint4", group_size=64), q.QWeightArgs(dtype="uint4", group_size=128, mse=True),
+                      q.QWeightArgs(dtype="int4", group_size=128, symmetric=True),
+                      q.QWeightArgs(dtype="uint4", group_size=128, clip_ratio=0.9)):
+            assert prequantized.lookup(_Value("w", w), other, "rtn") is None
+        assert prequantized.lookup(_Value("w", w), cfg.weights, "gptq") is None
+        x = rng.standard_normal((8, 16, 256)).astype(np.float32)
+        gcfg = q.QConfig(weights=q.QWeightArgs(dtype="uint4", group_size=128, algorithm=q.GPTQConfig()))
+        g = gcfg.weights.algorithm.quantize_weights(_Value("w", w), gcfg, out=_Value("y", node=_Node({"input": x})))
+        assert g is not merged["w"]
+    with pytest.raises(ValueError, match="layout='kn'"):
+        quantize_weights_sharded({"w": w}, RtnSpec(q.QuantType.QUInt4, "group", 128, layout="matmul_nbits"))
+
+
+def test_array_level_functions_accept_the_reference_packages_own_enums(cuda, rng):
+    """Patched into the reference (`integration.patched_reference`), `_rtn_quantize` /
+    `_gptq_quantize` receive the REFERENCE's `QuantType` / `QuantizationStrategy` members — other
+    classes with the same member names (the reference cannot travel to the GPU box, so stand-ins
+    with its definitions are used: core/_dtypes.py:33-41, core/_qconfig.py:31-36)."""
+    import enum
+
+    from onnx_quantize_b200.core._algorithms.gptq import _gptq_quantize
+    from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
+
+    class QuantizationStrategy(str, enum.Enum):          # noqa: N801 - the reference's class name
+        TENSOR = "tensor"
+        CHANNEL = "channel"
+        GROUP = "group"
+
+    class QuantType(enum.Enum):
+        QInt4 = 22
+        QUInt4 = 21
+        QInt8 = 3
+        QUInt8 = 2
+
+    w = (rng.standard_normal((128, 48)) * 0.05).astype(np.float32)
+    got = _rtn_quantize(w, QuantType.QUInt4, QuantizationStrategy.GROUP, 64, False, False, 1.0, False,
+                        np.dtype(np.float32), np.dtype(q.QuantType.QUInt4.np_dtype))
+    want = O.rtn_quantize(w, "uint4", "group", 64)
+    assert np.array_equal(as_i8(got[0], "uint4"), as_i8(want[0], "uint4")) and np.array_equal(bits(got[1]), bits(want[1]))
+    x = rng.standard_normal((8, 16, 128)).astype(np.float32)
+    got = _gptq_quantize(w, x, quant_type=QuantType.QInt8, strategy=QuantizationStrategy.CHANNEL, group_size=-1,
+                         is_symmetric=True, zp_dtype=np.dtype(np.int8))
+    want = O.gptq_quantize(w, x, "int8", "channel", -1, True)
+    assert np.array_equal(as_i8(got[0], "int8"), as_i8(want[0], "int8")) and np.array_equal(bits(got[1]), bits(want[1]))
+    with pytest.raises(AssertionError):
+        _rtn_quantize(w, QuantType.QUInt4, "group", 64, False, False, 1.0, False, np.dtype(np.float32), None)
