@@ -38,7 +38,8 @@ enum b200q_status {
   B200Q_ERR_UNSUPPORTED = -2,
   B200Q_ERR_WORKSPACE = -3,
   B200Q_ERR_CUDA = -4,
-  B200Q_NOT_POSITIVE_DEFINITE = 1 /* Cholesky hit a non-positive pivot: gptq.py:143-150 */
+  B200Q_NOT_POSITIVE_DEFINITE = 1, /* Cholesky hit a non-positive pivot: gptq.py:143-150 */
+  B200Q_MARGINAL_PIVOT = 2 /* bit flag OR-ed into the device status of b200q_hinv_cholesky_upper */
 };
 
 /* core/_dtypes.py:33-41 (QuantType) */
@@ -242,8 +243,12 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
  *   U       (K,K) f32 out: upper triangular, U^T U = (H[perm][:,perm] + damp*I)^-1
  *   perm    int32[K] out: row order of the loop (identity unless actorder)
  *   dead    uint8[K] out: 1 where diag(H) == 0 (the caller zeroes those rows of W, gptq.py:121)
- *   status  int32[1] out (device): 0, or B200Q_NOT_POSITIVE_DEFINITE — U is then the identity,
- *           the reference's "fall back to round-to-nearest" (gptq.py:143-150)
+ *   status  int32[1] out (device), bit flags: B200Q_NOT_POSITIVE_DEFINITE — U is then the identity,
+ *           the reference's "fall back to round-to-nearest" (gptq.py:143-150); B200Q_MARGINAL_PIVOT
+ *           (tensor-core precisions only) — a pivot fell below 1e-4 of its diagonal entry, which the
+ *           ~1e-5 relative error of the TF32x3 block products does not resolve: whether LAPACK's
+ *           float32 spotrf would have failed is then undecided and the caller should repeat the call
+ *           with B200Q_FP32_SIMT (the Python mirror does)
  * One Cholesky and one triangular inverse of the index-reversed matrix give the same U as the
  * reference's three LAPACK calls; the block products run through the tensor cores
  * with `precision` (B200Q_TF32X3 recommended; B200Q_FP32_SIMT = CUDA cores). */

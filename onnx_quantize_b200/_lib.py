@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200quant.so")
 # enums of include/b200q.h
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 NOT_POSITIVE_DEFINITE = 1
+MARGINAL_PIVOT = 2
 QTYPE = {"int4": 0, "uint4": 1, "int8": 2, "uint8": 3}
 STRATEGY = {"tensor": 0, "channel": 1, "group": 2}
 LAYOUT = {"kn": 0, "packed_flat": 1, "matmul_nbits": 2}

@@ -616,10 +616,13 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       B200Q_REQUIRE(bcr == CUDA_SUCCESS, B200Q_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 planes) failed (%d)", (int)bcr);
       // Tokens per unit = length of the truncating TMEM accumulation chain before a round-to-nearest
-      // reduction into H.  Measured (tools/prof_hessian_unit.py, max relative error vs float64):
-      // 512 -> 5e-6, 1024 -> 7e-6, 2048 -> 1.25e-5, 4096 -> 2.2e-5.  Every unit costs a 128 KB
-      // read-modify-write of H, which for K >= 2048 (H far larger than L2) is worth halving: +5 %.
-      int64_t chunk_stages = (K >= 2048 ? 2048 : 1024) / kBfTT;
+      // reduction into H.  Measured on B200 (tools/explore_gptq_parity.py `unit`, K = 4096, max relative
+      // error vs float64 / fraction of int4 codes of the strongly correlated 4096 x 4096 GPTQ chain that
+      // differ from the oracle's): 256 -> 3.8e-6 / 5.1e-4, 512 -> 4.8e-6 / 5.8e-4, 1024 -> 7.3e-6 / 6.9e-4,
+      // 2048 -> 1.3e-5 / 9.6e-4, 4096 -> 2.5e-5 / 1.4e-3 (the north_star gate is 1e-3).  Every unit
+      // costs a 128 KB read-modify-write of H; round 1 used 2048 tokens for K >= 2048 (+5 % Hessian
+      // throughput), which left no margin under the parity gate.
+      int64_t chunk_stages = 1024 / kBfTT;
       if (const char* e = getenv("B200Q_HESSIAN_BF16_UNIT")) {   // experiment knob (tokens per MMA unit)
         const long v = atol(e);
         if (v >= kBfTT) chunk_stages = v / kBfTT;

@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kNB = 128;            // block size of the factorization
 constexpr int kPitch = kNB + 1;     // shared-memory row pitch (conflict-free column access)
+constexpr float kMarginalPivot = 1e-4f;   // see chol_diag_kernel
 
 // ---- diagonal statistics: dead channels, damping ------------------------------------------------
 // out_diag[i] = diag with dead entries set to 1 (gptq.py:119-120); *damp = percdamp * mean(diag)
@@ -86,9 +87,19 @@ __global__ void gather_reverse_kernel(const float* __restrict__ H, int64_t K,
 // thread on values broadcast through a 128-float row (and column) buffer — two barriers per step,
 // no shared-memory traffic for the matrix itself.  The inverse V = C^-1 uses the same outer-product
 // form run backwards: T = I; for k = n-1 .. 0: V[k,:] = T[k,:] / C[k,k]; T[r,:] -= C[r,k] V[k,:] (r < k).
+//
+// `marginal_tol` > 0 (the tensor-core split modes): a pivot below marginal_tol x its own diagonal
+// entry before elimination (diag[perm[K-1-row]] + damp) is smaller than what the ~1e-5 relative
+// error of the TF32x3 trailing updates resolves, so the positive-definite decision is not
+// trustworthy: status bit 1 is raised and the caller redoes the factor in fp32 arithmetic
+// (gptq_device.hinv_cholesky_upper), whose decisions follow LAPACK's float32 spotrf.
 __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A, int64_t ld, int64_t j0,
                                                            int nb, float* __restrict__ DI,
-                                                           int32_t* __restrict__ status) {
+                                                           int32_t* __restrict__ status,
+                                                           const float* __restrict__ diag,
+                                                           const int32_t* __restrict__ perm,
+                                                           const float* __restrict__ damp,
+                                                           float marginal_tol) {
   __shared__ float rowbuf[kNB], colbuf[kNB];
   __shared__ float s_piv;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -114,8 +125,11 @@ __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A
       __syncthreads();
       float piv = s_piv;
       if (!(piv > 0.0f)) {                // also catches NaN: LAPACK spotrf's `ajj <= 0 || isnan`
-        if (tid == 0) atomicExch(status, 1);
+        if (tid == 0) atomicOr(status, 1);
         piv = 1.0f;
+      } else if (marginal_tol > 0.0f && tid == 0) {
+        const float orig = diag[perm[ld - 1 - (j0 + k)]] + *damp;
+        if (piv < marginal_tol * orig) atomicOr(status, 2);
       }
       const float d = sqrtf(piv), inv = 1.0f / d;
       if (ty == kk) {
@@ -210,7 +224,7 @@ __global__ void reflect_kernel(const float* __restrict__ VT, int64_t K,
   const int64_t i = blockIdx.y;
   if (j >= K) return;
   float v;
-  if (*status != 0) v = (i == j) ? 1.0f : 0.0f;
+  if ((*status & 1) != 0) v = (i == j) ? 1.0f : 0.0f;
   else v = (j >= i) ? VT[(K - 1 - i) * K + (K - 1 - j)] : 0.0f;
   U[i * K + j] = v;
 }
@@ -287,7 +301,8 @@ int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int ac
   for (int64_t j0 = 0, jb = 0; j0 < K; j0 += kNB, ++jb) {
     const int nb = (int)(K - j0 < kNB ? K - j0 : kNB);
     float* DIj = ws.DI + jb * kNB * kNB;
-    chol_diag_kernel<<<1, 256, 0, st>>>(ws.Hr, K, j0, nb, DIj, status);
+    chol_diag_kernel<<<1, 256, 0, st>>>(ws.Hr, K, j0, nb, DIj, status, ws.diag, perm, ws.damp,
+                                        precision == B200Q_FP32_SIMT ? 0.0f : kMarginalPivot);
     B200Q_LAUNCH_OK();
     const int64_t rest = K - j0 - nb;
     if (rest <= 0) break;

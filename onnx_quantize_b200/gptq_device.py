@@ -21,12 +21,18 @@ class HinvFactor:
     u: torch.Tensor        # (K,K) f32 upper, UᵀU = (H[perm][:,perm] + damp·I)⁻¹ (identity on failure)
     perm: torch.Tensor     # (K,) int32 row order of the loop
     dead: torch.Tensor     # (K,) uint8, 1 where diag(H) == 0
-    status: torch.Tensor   # (1,) int32 on device: 0 or NOT_POSITIVE_DEFINITE
+    status: torch.Tensor   # (1,) int32 on device, bit flags NOT_POSITIVE_DEFINITE | MARGINAL_PIVOT
 
     @property
     def ok(self) -> bool:
         """True when the factorization succeeded (synchronises)."""
-        return int(self.status.item()) == 0
+        return (int(self.status.item()) & _lib.NOT_POSITIVE_DEFINITE) == 0
+
+    @property
+    def marginal(self) -> bool:
+        """True when a tensor-core precision met a pivot too small for it to decide positive
+        definiteness the way float32 LAPACK would (synchronises) — see ``resolve_marginal``."""
+        return (int(self.status.item()) & _lib.MARGINAL_PIVOT) != 0
 
 
 def hinv_cholesky_upper(h: torch.Tensor, percdamp: float = 0.01, actorder: bool = False,
@@ -48,6 +54,13 @@ def hinv_cholesky_upper(h: torch.Tensor, percdamp: float = 0.01, actorder: bool 
                                        ws.numel(), dev.stream_ptr())
     _lib.check(rc, "b200q_hinv_cholesky_upper")
     return HinvFactor(u, perm, dead, status)
+
+
+def resolve_marginal(f: HinvFactor, h: torch.Tensor, percdamp: float = 0.01, actorder: bool = False) -> HinvFactor:
+    """``f`` itself unless its status carries MARGINAL_PIVOT, in which case the factor is redone in
+    fp32 arithmetic (CUDA cores), whose accept / LinAlgError decisions follow LAPACK's float32
+    Cholesky (gptq.py:139-150).  Synchronises; call it where the host looks at the result anyway."""
+    return hinv_cholesky_upper(h, percdamp, actorder, "fp32") if f.marginal else f
 
 
 def gptq_quantize(w: torch.Tensor, f: HinvFactor, quant_type, strategy, group_size=-1,

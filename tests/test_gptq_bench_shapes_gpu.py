@@ -184,3 +184,23 @@ def test_mse_search_4096_g128_matches_oracle_bit_for_bit(cuda):
     differing = int(((s_np.view(np.uint32) != ws.view(np.uint32)) | (z_np != wz)).sum())
     assert differing == 0, f"{differing} of {ws.size} groups differ"
     assert np.array_equal(codes.cpu().numpy(), np.asarray(want[0]).astype(np.uint8))
+
+
+@pytest.mark.parametrize("percdamp", [1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 0.0])
+def test_marginal_pivots_are_decided_in_fp32_like_lapack(cuda, percdamp):
+    """A rank-deficient Hessian with (almost) no damping: the pivots of the null space are of the size
+    of float32 round-off, where the tensor-core split modes (1e-5 relative error in the trailing
+    updates) and LAPACK disagree (measured: LAPACK raises LinAlgError from percdamp = 1e-7 down, the
+    TF32x3 factorization never does).  The device flags such pivots (B200Q_MARGINAL_PIVOT) and the
+    factor is redone in fp32 arithmetic, which takes LAPACK's decision."""
+    k = 1024
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((k // 2, k)).astype(np.float32)
+    h32 = ((2.0 / x.shape[0]) * (x.T.astype(np.float64) @ x.astype(np.float64))).astype(np.float32)
+    _, ok_ref = O.hinv_cholesky_upper(h32, percdamp)
+    h = torch.from_numpy(h32).to(cuda)
+    f = G.hinv_cholesky_upper(h, percdamp, False, "bf16x3")
+    assert f.marginal                                     # every one of these cases is below the 1e-4 line
+    assert G.resolve_marginal(f, h, percdamp, False).ok == ok_ref
+    well = G.hinv_cholesky_upper(h, 0.01, False, "bf16x3")
+    assert well.ok and not well.marginal                  # the default damping is nowhere near it

@@ -176,3 +176,86 @@ def test_array_level_functions_accept_the_reference_packages_own_enums(cuda, rng
     assert np.array_equal(as_i8(got[0], "int8"), as_i8(want[0], "int8")) and np.array_equal(bits(got[1]), bits(want[1]))
     with pytest.raises(AssertionError):
         _rtn_quantize(w, QuantType.QUInt4, "group", 64, False, False, 1.0, False, np.dtype(np.float32), None)
+
+
+def test_gptq_plugin_shares_hessian_and_factor_between_nodes_with_the_same_input(cuda, rng):
+    """q/k/v read one activation: the reference stores the SAME array object in their
+    node.meta["input"] (calibrate.py:296-307).  The plugin must upload it, contract it and factorize
+    once — and return what three independent computations return."""
+    from onnx_quantize_b200 import _lib
+    from onnx_quantize_b200.core._algorithms.gptq import calibration_cache
+
+    lib = _lib.load()
+    k = 256
+    x = rng.standard_normal((16, 24, k)).astype(np.float32)
+    ws = [(rng.standard_normal((k, n)) * 0.05).astype(np.float32) for n in (64, 32, 32)]
+    cfg = q.QConfig(weights=q.QWeightArgs(dtype="int4", group_size=128, symmetric=True,
+                                          algorithm=q.GPTQConfig(mode="propagate")))
+    calibration_cache.clear()
+    h0, m0, fh0, fm0 = (calibration_cache.hits, calibration_cache.misses, calibration_cache.factor_hits,
+                        calibration_cache.factor_misses)
+    launches, shared = [], []
+    for i, w in enumerate(ws):
+        before = lib.b200q_launch_count()
+        shared.append(cfg.weights.algorithm.quantize_weights(_Value(f"w{i}", w), cfg,
+                                                             out=_Value("y", node=_Node({"input": x}))))
+        launches.append(lib.b200q_launch_count() - before)
+    assert (calibration_cache.misses - m0, calibration_cache.hits - h0) == (1, 2)
+    assert (calibration_cache.factor_misses - fm0, calibration_cache.factor_hits - fh0) == (1, 2)
+    assert launches[1] < launches[0] and launches[2] < launches[0]      # no Hessian / factor launches again
+    for w, got in zip(ws, shared):                                       # same results as without sharing
+        calibration_cache.clear()
+        alone = cfg.weights.algorithm.quantize_weights(_Value("w", w), cfg,
+                                                       out=_Value("y", node=_Node({"input": x.copy()})))
+        assert np.array_equal(as_i8(got[0], "int4"), as_i8(alone[0], "int4"))
+        assert np.array_equal(bits(got[1]), bits(alone[1]))
+    # a different array object with other contents, or an in-place edit, is a different input
+    calibration_cache.clear()
+    m1 = calibration_cache.misses
+    cfg.weights.algorithm.quantize_weights(_Value("w", ws[0]), cfg, out=_Value("y", node=_Node({"input": x})))
+    x *= np.float32(1.5)
+    cfg.weights.algorithm.quantize_weights(_Value("w", ws[0]), cfg, out=_Value("y", node=_Node({"input": x})))
+    assert calibration_cache.misses - m1 == 2
+    calibration_cache.clear()
+
+
+def test_streamed_hessian_from_host_chunks_matches_one_shot(cuda, rng, monkeypatch):
+    """Host activations larger than one staging chunk are folded chunk by chunk (alpha = 2/n, beta = 1):
+    same H as one call on the whole array, to float32 accumulation order."""
+    import torch
+
+    from onnx_quantize_b200.core._algorithms import gptq as gq
+    from onnx_quantize_b200.hessian import hessian_accumulate
+    k = 256
+    x = rng.standard_normal((12, 700, k)).astype(np.float32)
+    monkeypatch.setattr(gq, "_HESSIAN_CHUNK_BYTES", 1024 * 4 * k)       # 1024-row chunks -> 9 chunks, ragged tail
+    h = gq._hessian_from_host(x, k, "bf16x3")
+    want = torch.zeros((k, k), device=cuda)
+    hessian_accumulate(torch.from_numpy(x).to(cuda), want, alpha=2.0 / 12, beta=0.0, precision="bf16x3")
+    assert ((h - want).abs().max() / want.abs().max()).item() < 1e-5
+    ref, _ = O.accumulate_hessian(x, np.zeros((k, k), np.float32), 0)
+    assert np.abs(h.cpu().numpy() - ref).max() / np.abs(ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("dtype,sym,gs,shape", [("uint4", False, 128, (2304, 2048)), ("int4", True, 64, (2048, 2048)),
+                                                ("int8", False, 256, (4096, 1536))])
+def test_streamed_single_call_path_is_bit_exact(cuda, dtype, sym, gs, shape):
+    """Weights of 16 MB and more take the chunk-pipelined route inside `_rtn_quantize` (upload of row
+    chunk c, kernels of chunk c-1 and download of chunk c-2 overlap; ragged last chunk; parameters
+    scattered into the reference's (N*G, 1) order): identical to the oracle, and to the plain route."""
+    from onnx_quantize_b200 import pipeline
+    from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
+    rng = np.random.default_rng(shape[0] + gs)
+    w = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    assert pipeline.streamed_chunk_rows(*shape, gs) > 0
+    qt = q.QuantType.from_string(dtype)
+    got = _rtn_quantize(w, qt, q.QuantizationStrategy.GROUP, gs, sym, False, 0.9, False, np.dtype(np.float32), qt.np_dtype)
+    want = O.rtn_quantize(w, dtype, "group", gs, sym, False, 0.9, False)
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype and a.shape == b.shape
+    assert np.array_equal(as_i8(got[0], dtype), as_i8(want[0], dtype))
+    assert np.array_equal(bits(got[1]), bits(want[1])) and np.array_equal(as_i8(got[2], dtype), as_i8(want[2], dtype))
+    # twice in a row (staging chunks and events are reused), and from a read-only view
+    w.setflags(write=False)
+    again = _rtn_quantize(w, qt, q.QuantizationStrategy.GROUP, gs, sym, False, 0.9, False, np.dtype(np.float32), qt.np_dtype)
+    assert all(np.array_equal(np.asarray(a).view(np.uint8), np.asarray(b).view(np.uint8)) for a, b in zip(got, again))
