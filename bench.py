@@ -54,8 +54,8 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gptq", action="store_true")
-    p.add_argument("--gptq-layers", type=int, default=8,
-                   help="Llama-3-8B-shaped layers in the GPTQ sample (the model has 32)")
+    p.add_argument("--gptq-layers", type=int, default=0,
+                   help="layers in the GPTQ variants (0 = every layer of the model: 32 Llama-3-8B / 26 Gemma-3-1B)")
     p.add_argument("--gptq-precision", default="bf16x3", choices=["tf32", "tf32x3", "bf16x3"])
     p.add_argument("--gptq-streams", type=int, default=8,
                    help="CUDA streams the independent GPTQ solves of a rank are spread over")
@@ -237,13 +237,9 @@ def gptq_cpu_reference(groups, model_layers):
 
 def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", layers=None, cpu_ref=False):
     model_layers, GPTQ_GROUPS = GPTQ_MODELS[model]
-    from onnx_quantize_b200 import gptq_device as G
-    from onnx_quantize_b200.core._dtypes import QuantType
-    from onnx_quantize_b200.hessian import hessian_accumulate
-    from onnx_quantize_b200.parallel.shard import assign_units
-    from onnx_quantize_b200.parallel.streams import StreamPool
+    from onnx_quantize_b200.parallel.gptq_pipeline import GptqPipeline, GptqSpec, GptqUnit
 
-    layers = layers or args.gptq_layers
+    layers = layers or args.gptq_layers or model_layers
     tokens = GPTQ_SAMPLES * GPTQ_SEQ
     t_local = tokens // world
     gen = torch.Generator(device=device)
@@ -256,59 +252,30 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
             if shp not in ws:
                 ws[shp] = torch.randn(shp, generator=gen, device=device, dtype=torch.float32) * 0.02
     units = [(l, gi) for l in range(layers) for gi in range(len(GPTQ_GROUPS))]
-    costs = [GPTQ_GROUPS[gi][1] ** 3 * 2.0 / 3 + sum(k * k * n for k, n in GPTQ_GROUPS[gi][2]) for _, gi in units]
-    plan = assign_units(costs, world)
-    owner = {}
-    for r, idxs in enumerate(plan):
-        for i in idxs:
-            owner[units[i]] = r
-    alpha = 2.0 / GPTQ_SAMPLES
-    hs = {}
-    pool = StreamPool(args.gptq_streams, device)
+    # the layers are identical in shape: one token tensor per K and one weight tensor per shape stand
+    # for all of them (every unit still gets its own Hessian, factor and results)
+    punits = [GptqUnit(f"l{l}.{GPTQ_GROUPS[gi][0]}", GPTQ_GROUPS[gi][1], [ws[shp] for shp in GPTQ_GROUPS[gi][2]],
+                       xs[GPTQ_GROUPS[gi][1]], GPTQ_SAMPLES) for l, gi in units]
+    spec = GptqSpec("int4", "group", 128, True, False, 1.0, False, 128, 0.01, False, "propagate", args.gptq_precision)
+    pipe = GptqPipeline(args.gptq_streams, device)
 
-    def ev():
-        e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        return e
-
-    def one_step():
-        e0 = ev()
-        for u in units:                                    # G1: every rank, its share of the tokens
-            k = GPTQ_GROUPS[u[1]][1]
-            h = hs.get(u)
-            if h is None:
-                h = hs[u] = torch.empty((k, k), dtype=torch.float32, device=device)
-            hessian_accumulate(xs[k], h, alpha=alpha, beta=0.0, precision=args.gptq_precision)
-        e1 = ev()
-        if world > 1:                                      # the exchange step: sum to the owner
-            for u in units:
-                dist.reduce(hs[u], dst=owner[u], op=dist.ReduceOp.SUM)
-        e2 = ev()
-        def solve(u):                                      # G2-G4 of one Hessian group
-            def job():
-                f = G.hinv_cholesky_upper(hs[u], 0.01, False, args.gptq_precision)
-                return [G.gptq_quantize(ws[shp], f, QuantType.QInt4, "group", 128, True, False, 1.0, False, 128,
-                                        "propagate", args.gptq_precision) for shp in GPTQ_GROUPS[u[1]][2]]
-            return job
-
-        mine = [i for i, u in enumerate(units) if owner[u] == rank]      # on the owner, side by side
-        pool.run([solve(units[i]) for i in mine], [costs[i] for i in mine])
-        e3 = ev()
-        return e0, e1, e2, e3
-
-    one_step()                                             # warm-up (workspaces, attributes)
+    run = pipe.run(punits, spec)                           # warm-up (workspaces, attributes, NCCL channels)
+    del run
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1, e2, e3 = one_step()
+    run = pipe.run(punits, spec)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e3), e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)],
+    e0, e1, e2, e3 = run.start, run.hessians_done, run.reduces_done, run.end
+    t = torch.tensor([e0.elapsed_time(e3), e0.elapsed_time(e1), e1.elapsed_time(e2), e1.elapsed_time(e3)],
                      device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, hess_ms, red_ms, solve_ms = (float(v) for v in t)
+    n_failed = sum(0 if f.ok else 1 for f in run.factors.values())
+    del run
     flops = sum(2.0 * tokens * GPTQ_GROUPS[gi][1] ** 2 for _, gi in units)     # de-duplicated by input
 
     def executed(k):   # the kernel only computes the 128x256 tiles that touch the upper triangle
@@ -328,13 +295,18 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
     is_bf16 = args.gptq_precision == "bf16x3"
     mma_peak = bf16 if is_bf16 else bf16 / 2
     out = {
-        "workload": f"GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} "
+        "workload": f"GPTQ int4 sym g128 (block 128, percdamp 0.01, mode=propagate) on {layers} of {model_layers} "
                     f"{model}-shaped layers ({len(units)} Hessians, {7 * layers} weights), "
                     f"{GPTQ_SAMPLES}x{GPTQ_SEQ} calibration tokens split over {world} rank(s)",
         "precision": args.gptq_precision, "solve_streams": args.gptq_streams, "scaling": "strong", "n_gpus": world,
         "s_per_step": total_ms * 1e-3, "s_per_model_extrapolated": total_ms * 1e-3 * model_layers / layers,
         "extrapolation": f"x{model_layers / layers:g}: the {model_layers} layers are identical in shape",
-        "hessian_s": hess_ms * 1e-3, "hessian_reduce_s": red_ms * 1e-3, "solve_s": solve_ms * 1e-3,
+        "hessian_s": hess_ms * 1e-3, "solve_s": solve_ms * 1e-3,
+        "hessian_reduce_s_under_solves": red_ms * 1e-3,
+        "phases": "hessian_s = every unit's Hessian on this rank's tokens; then the NCCL reduces to the owners run on "
+                  "a communication stream UNDERNEATH the solves (each solve waits for its own unit's reduce only): "
+                  "solve_s spans both, hessian_reduce_s_under_solves is when the last reduce finished",
+        "factorizations_failed": n_failed,
         "hessian_tflops_algorithmic": flops / (hess_ms * 1e-3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "hessian_bf16x3_kernel" if is_bf16 else "hessian_kernel",
                      "achieved": tf, "unit": "TFLOP/s", "peak": mma_peak, "frac": tf / mma_peak,
@@ -346,7 +318,10 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
                                      "tiles only, x3 products in 3xTF32 mode) / Hessian time"),
                      "flops": flops},
     }
-    del xs, ws, hs
+    del xs, ws, punits
+    pipe.release()
+    from onnx_quantize_b200 import device_api as D
+    D.dev.release_workspaces()
     torch.cuda.empty_cache()
     if cpu_ref and rank == 0:
         out["cpu_reference"] = gptq_cpu_reference(GPTQ_GROUPS, model_layers)
@@ -505,6 +480,204 @@ def run_cfg3_mlp(torch, dist, device, world, rank):
                                  "peak = measured sustained bf16"}}
 
 
+# ------------------------------------------------------------------------------------------------
+# The reference-facing seam, measured as the reference drives it (qrules/_common.py:133): one
+# `qconfig.weights.algorithm.quantize_weights(w, qconfig)` call per initializer with the PAGEABLE
+# NumPy array `w.const_value.numpy()` delivers, NumPy results back, single-threaded caller.
+# ------------------------------------------------------------------------------------------------
+class _Const:
+    def __init__(self, a):
+        self._a = a
+
+    def numpy(self):
+        return self._a
+
+
+class _Value:                      # ir.Value: .name, .const_value.numpy(), .producer()
+    def __init__(self, name, a=None, node=None):
+        self.name, self.const_value, self._node = name, _Const(a), node
+
+    def producer(self):
+        return self._node
+
+
+class _Node:                       # ir.Node: .meta
+    def __init__(self, meta):
+        self.meta = meta
+
+
+def _pageable_layer(rank):
+    rng = np.random.default_rng(500 + rank)
+    return [rng.standard_normal((k, n), dtype=np.float32) * np.float32(0.02) for _, k, n in LLAMA3_8B_LAYER]
+
+
+def run_plugin_e2e(args, torch):
+    """cfg2 through the plugin seam, two ways: (a) plugin calls alone, one weight at a time; (b) the
+    pre-pass the package offers for exactly this (parallel.shard.quantize_weights_sharded publishes
+    reference-shaped triples, the plugin calls that follow are look-ups) — timed INCLUDING the 224
+    plugin calls.  Inputs: 7 distinct pageable float32 arrays (one Llama-3-8B-shaped layer) visited
+    once per layer of the model; every call returns fresh NumPy arrays, all 224 results are kept
+    alive until the step ends, as the rewriter keeps its initializers."""
+    import onnx_quantize_b200 as q
+    from onnx_quantize_b200.parallel import prequantized
+    from onnx_quantize_b200.parallel.shard import quantize_weights_sharded
+    from onnx_quantize_b200.pipeline import RtnSpec
+
+    layer = _pageable_layer(0)
+    names = [f"model.layers.{l}.{nm}.weight" for l in range(args.layers) for nm, _, _ in LLAMA3_8B_LAYER]
+    arrays = [layer[j] for _ in range(args.layers) for j in range(len(layer))]
+    in_bytes = sum(a.nbytes for a in arrays)
+    cfg = q.QConfig(weights=q.QWeightArgs(dtype="uint4", group_size=128, symmetric=False, mse=True, clip_ratio=0.9))
+    plugin = cfg.weights.algorithm
+
+    def direct():
+        return [plugin.quantize_weights(_Value(nm, a), cfg) for nm, a in zip(names, arrays)]
+
+    def with_prepass():
+        with prequantized.scope():
+            quantize_weights_sharded(dict(zip(names, arrays)), RtnSpec.from_weight_args(cfg.weights))
+            return [plugin.quantize_weights(_Value(nm, a), cfg) for nm, a in zip(names, arrays)]
+
+    out = {}
+    for key, fn, api in (("plugin_calls", direct, "RTNConfig.quantize_weights(w, qconfig) per initializer, nothing else"),
+                         ("prepass_then_plugin_calls", with_prepass,
+                          "parallel.shard.quantize_weights_sharded (bulk pipeline, results published) followed by the same "
+                          "224 RTNConfig.quantize_weights calls (look-ups keyed by name + request digest + weight fingerprint)")):
+        res = fn()                                                 # warm-up (staging, pinned pool, workspaces)
+        d2h = sum(sum(np.asarray(x).nbytes for x in r) for r in res)
+        del res
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        del res
+        out[key] = {"value": in_bytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": d2h, "api": api}
+    out["note"] = ("pageable NumPy in, NumPy (reference dtypes/shapes, (K,N) codes one byte per element) out; the host "
+                   "side is bound by memcpy into pinned staging (35-60 GB/s on these hosts) and by the first-touch page "
+                   "faults of the 7.0 GB of fresh result arrays (17-37 GB/s), see DESIGN.md §6")
+    return out
+
+
+def run_gptq_plugin_e2e(args, torch, device):
+    """One Llama-3-8B-shaped layer through `GPTQConfig.quantize_weights` exactly as the rewriter calls
+    it: host float32 weights, host calibration activations in node.meta["input"] — 128 x 2048 tokens per
+    distinct layer input, the SAME array object for q/k/v and for gate/up (calibrate.py:296-307) —
+    host codes/scales/zero points back.  Activations are generated on the device and copied to
+    pageable host memory before the timed region."""
+    import onnx_quantize_b200 as q
+    from onnx_quantize_b200 import _lib
+    from onnx_quantize_b200.core._algorithms.gptq import calibration_cache
+
+    lib = _lib.load()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(99)
+
+    def host_tokens(k):
+        x = torch.empty((GPTQ_SAMPLES, GPTQ_SEQ, k), dtype=torch.float32)
+        for s0 in range(0, GPTQ_SAMPLES, 16):
+            x[s0:s0 + 16] = torch.randn((16, GPTQ_SEQ, k), generator=gen, device=device).cpu()
+        return x.numpy()
+
+    inputs = {"qkv": host_tokens(4096), "o": host_tokens(4096), "gate_up": host_tokens(4096), "down": host_tokens(14336)}
+    use = {"q": "qkv", "k": "qkv", "v": "qkv", "o": "o", "gate": "gate_up", "up": "gate_up", "down": "down"}
+    layer = _pageable_layer(1)
+    cfg = q.QConfig(weights=q.QWeightArgs(dtype="int4", group_size=128, symmetric=True,
+                                          algorithm=q.GPTQConfig(mode="propagate", precision=args.gptq_precision)))
+    plugin = cfg.weights.algorithm
+
+    def step():
+        calibration_cache.clear()
+        return [plugin.quantize_weights(_Value(nm, w), cfg, out=_Value("y", node=_Node({"input": inputs[use[nm]]})))
+                for (nm, _, _), w in zip(LLAMA3_8B_LAYER, layer)]
+
+    step()
+    torch.cuda.synchronize()
+    launches0 = lib.b200q_launch_count()
+    m0 = calibration_cache.misses
+    t0 = time.perf_counter()
+    res = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    h2d = sum(x.nbytes for x in inputs.values()) + sum(w.nbytes for w in layer)
+    d2h = sum(sum(np.asarray(x).nbytes for x in r) for r in res)
+    calibration_cache.clear()
+    return {"workload": "GPTQ int4 sym g128 of ONE Llama-3-8B-shaped layer through GPTQConfig.quantize_weights: 7 plugin "
+                        "calls, host weights + host activations (4 distinct inputs of 128x2048 tokens, q/k/v and gate/up "
+                        "share theirs) in, host results out",
+            "s_per_layer": dt, "s_per_model_extrapolated": dt * 32, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "h2d_gbs": h2d / dt / 1e9, "hessians_computed": calibration_cache.misses - m0,
+            "gpu_launches": int(lib.b200q_launch_count() - launches0),
+            "api": "GPTQConfig.quantize_weights(w, qconfig, out=out) with node.meta['input'] (pageable NumPy)",
+            "note": "28.3 GB of calibration activations cross PCIe once per distinct input (the reference keeps them in "
+                    "host RAM); the step is bound by that upload"}
+
+
+def run_cfg2_strong(args, torch, dist, device, world, rank, weights):
+    """The weight-sharding axis (SURVEY.md §8e first bullet): ONE Llama-3-8B-shaped set quantized by all
+    ranks together.  (a) device-resident shards, one batched launch per rank, CUDA events, max over
+    ranks; (b) end to end through parallel.shard.quantize_weights_sharded: every rank uploads its
+    share from (pageable) host memory, packed results travel to rank 0 as tensors over NCCL and are
+    copied to the host once — wall clock between barriers, max over ranks."""
+    from onnx_quantize_b200 import device_api as D
+    from onnx_quantize_b200.core._dtypes import QuantType
+    from onnx_quantize_b200.parallel.shard import assign_units, quantize_weights_sharded
+    from onnx_quantize_b200.pipeline import RtnSpec
+
+    layer = _pageable_layer(0)                               # identical on every rank
+    names = [f"model.layers.{l:02d}.{nm}.weight" for l in range(args.layers) for nm, _, _ in LLAMA3_8B_LAYER]
+    named = {nm: layer[i % len(layer)] for i, nm in enumerate(names)}   # 7 distinct arrays, visited once per layer
+    costs = [w.numel() for w in weights]                     # the rank's resident set stands for the one model
+    mine = assign_units(costs, world)[rank]
+    shard = [weights[i] for i in mine]
+    plan = D.RtnBatchPlan(shard, QuantType.QUInt4, "group", 128, False, False, 0.9, True, layout="matmul_nbits")
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        plan.run()
+    sync_all()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        plan.run()
+    b.record()
+    sync_all()
+    t = torch.tensor([a.elapsed_time(b) / 3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t[0])
+    del plan, shard
+    spec = RtnSpec(QuantType.QUInt4, "group", 128, False, False, 0.9, True, "kn")
+    quantize_weights_sharded(named, spec, publish=False)     # warm-up
+    sync_all()
+    t0 = time.perf_counter()
+    res = quantize_weights_sharded(named, spec, publish=False)
+    sync_all()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    d2h = sum(sum(np.asarray(x).nbytes for x in r) for r in res.values()) if res else 0
+    del res
+    torch.cuda.empty_cache()
+    in_bytes = 4 * sum(costs)
+    return {"workload": "cfg2 (RTN uint4 asym g128 + MSE) on ONE Llama-3-8B-shaped set sharded over the ranks by weight "
+                        "matrix (largest first), no data-path collective", "scaling": "strong", "n_gpus": world,
+            "device": {"ms_per_step": dev_ms, "value": in_bytes / (dev_ms * 1e-3) / 1e9, "unit": "GB/s",
+                       "timing": "CUDA events around one batched launch over the rank's shard, max over ranks"},
+            "e2e": {"ms_per_step": dt * 1e3, "value": in_bytes / dt / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_on_rank0": d2h,
+                    "api": "parallel.shard.quantize_weights_sharded(named pageable weights, RtnSpec(layout='kn')): "
+                           "results gathered on rank 0 as packed tensors over NCCL, one D2H there",
+                    "timing": "wall clock between barriers, max over ranks"}}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -612,8 +785,14 @@ def run_gpu_arm(args):
                "ms_per_step": e2e_s * 1e3,
                "pcie_h2d_gbs_measured_per_gpu": h2d_gbs,
                "frac_of_pcie_h2d": (in_bytes / e2e_s / 1e9) / h2d_gbs,
-               "api": "onnx_quantize_b200.pipeline.quantize_weights_bulk (pinned host weights in, host results out)"}
+               "api": "onnx_quantize_b200.pipeline.quantize_weights_bulk (PINNED host weights in, pinned-backed host results "
+                      "out; the bulk pipeline the multi-GPU pre-pass runs on each rank) — NOT the per-initializer plugin "
+                      "call: that is e2e_plugin",
+               "host_inputs": "7 distinct pinned matrices (one Llama-3-8B-shaped layer), revisited once per layer of the "
+                              "model: every step moves all 27.9 GB across PCIe"}
 
+    strong = run_cfg2_strong(args, torch, dist, device, world, rank, weights)
+    plugin = run_plugin_e2e(args, torch) if (world == 1 and not args.no_e2e) else None
     small = run_small_variants(torch, device, measured_peaks()[0]) if rank == 0 else None
     cfg3 = run_cfg3_mlp(torch, dist, device, world, rank)
     if small is not None:
@@ -624,10 +803,13 @@ def run_gpu_arm(args):
         D.dev.release_workspaces()
         torch.cuda.empty_cache()
         want_cpu = not args.no_cpu_baseline and world == 1
-        gptq = {"gptq_int4_g128_llama3_8b": run_gptq_variant(args, torch, dist, device, world, rank, "llama3_8b",
+        gptq = {}
+        if world == 1 and not args.no_e2e:
+            gptq["gptq_int4_g128_llama3_8b_layer_e2e_plugin"] = run_gptq_plugin_e2e(args, torch, device)
+        gptq = {**gptq,
+                "gptq_int4_g128_llama3_8b": run_gptq_variant(args, torch, dist, device, world, rank, "llama3_8b",
                                                              cpu_ref=want_cpu),
-                "gptq_int4_g128_gemma3_1b": run_gptq_variant(args, torch, dist, device, world, rank, "gemma3_1b",
-                                                             layers=26)}
+                "gptq_int4_g128_gemma3_1b": run_gptq_variant(args, torch, dist, device, world, rank, "gemma3_1b")}
 
     if rank != 0:
         if world > 1:
@@ -644,11 +826,12 @@ def run_gpu_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_mse,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "b200",
-        "config": {"workload": WORKLOAD if args.layers == N_LAYERS else WORKLOAD + f" [{args.layers} layers]",
-                   "elements_per_gpu": elts, "input_bytes_per_gpu": in_bytes,
-                   "parallelism": f"{world} rank(s), one model-sized set each, no collective",
-                   "cache": "inputs (27.9 GB) larger than L2; no flush needed",
-                   "host_cores_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
+        "config": {"workload": WORKLOAD if args.layers == N_LAYERS else WORKLOAD + f" [{args.layers} layers]"},
+        "config_detail": {"elements_per_gpu": elts, "input_bytes_per_gpu": in_bytes,
+                          "parallelism": f"{world} rank(s), one model-sized set each, no collective (replicas: the "
+                                         "strong-scaling figures are variants.cfg2_strong_weight_sharding and the GPTQ variants)",
+                          "cache": "inputs (27.9 GB) larger than L2; no flush needed",
+                          "host_cores_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": 243.74e6,
@@ -683,6 +866,9 @@ def run_gpu_arm(args):
         "wall_ms_per_step": wall_mse * 1e3,
         "clocks": sampler.summary() if sampler else None,
     }
+    line["variants"]["cfg2_strong_weight_sharding"] = strong
+    if plugin:
+        line["e2e_plugin"] = plugin
     if small:
         line["variants"].update(small)
     if gptq:
@@ -710,7 +896,8 @@ def main():
             "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": {"workload": WORKLOAD},
+            "config_detail": {"sample": sample},
             "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }), flush=True)

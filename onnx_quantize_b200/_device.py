@@ -65,9 +65,11 @@ _STAGE_CHUNK_ELEMS = (32 << 20) // 4
 
 def _default_stage_threads() -> int:
     """Host threads that move bytes between pageable arrays and the pinned staging chunks.  Measured
-    on the 16-core B200 host (tools/prof_host_copy.py): pageable -> pinned saturates at 52-60 GB/s
-    from 4 threads on, pinned -> a FRESH pageable array (first-touch page faults) keeps scaling to
-    37 GB/s at 12 threads; two cores are left to the caller and the CUDA driver threads."""
+    on the 16-core B200 hosts (tools/prof_host_copy.py, tools/prof_upload.py): pageable -> pinned
+    runs at 35-60 GB/s from 4 threads on (it varies that much from box to box), pinned -> a FRESH
+    pageable array (first-touch page faults) at 17-37 GB/s; with the chunk DMA pipelined behind the
+    fill, 8 threads gave the shortest upload of a 235 MB weight (7.1 ms; 4 threads 8.3, 12 threads
+    8.4)."""
     import os
 
     env = os.environ.get("B200Q_STAGE_THREADS")
@@ -77,7 +79,7 @@ def _default_stage_threads() -> int:
         avail = len(os.sched_getaffinity(0))
     except (AttributeError, OSError):
         avail = os.cpu_count() or 4
-    return max(2, min(12, avail - 2))
+    return max(2, min(8, avail - 2))
 
 
 _STAGE_THREADS = _default_stage_threads()

@@ -67,12 +67,6 @@ def _rtn_quantize(array: np.ndarray, quant_type: QuantType, strategy: Quantizati
     """
     strategy = coerce_strategy(strategy)
     quant_type = QuantType.coerce(quant_type)
-    if strategy == QuantizationStrategy.GROUP and not mse:      # large weights: the call's three legs overlapped
-        from onnx_quantize_b200.pipeline import rtn_quantize_streamed
-
-        raw = rtn_quantize_streamed(array, quant_type, group_size, is_symmetric, reduce_range, clip_ratio)
-        if raw is not None:
-            return _finalize_triple(*raw, quant_type, strategy, scale_dtype, zp_dtype)
     w = dev.to_device_f32(array)
     if w.dim() != 2:
         raise ValueError("weights must be 2-D (in_channels, out_channels)")

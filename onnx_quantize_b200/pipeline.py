@@ -207,130 +207,3 @@ def result_bytes(results) -> int:
     return int(sum(sum(a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size()
                        for a in r) for r in results))
 
-
-# ------------------------------------------------------------------------------------------------
-# One weight per call, pageable NumPy in, NumPy out — the plugin seam itself (qrules/_common.py:133
-# hands `w.const_value.numpy()` to `quantize_weights`, one weight at a time, and waits for the result)
-# ------------------------------------------------------------------------------------------------
-_STREAM_MIN_BYTES = 16 << 20
-_DOWN_CHUNK_BYTES = 16 << 20
-
-
-class _HostPipe:
-    """Per-device streams, events and pinned down-staging for ``rtn_quantize_streamed``."""
-
-    def __init__(self, device):
-        self.h2d, self.d2h = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-        self.down = [torch.empty((_DOWN_CHUNK_BYTES,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-        self.down_np = [b.numpy() for b in self.down]
-        self.down_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        self.lock = threading.Lock()
-
-
-_PIPES: dict[int, _HostPipe] = {}
-
-
-def _host_pipe(device) -> _HostPipe:
-    with _SLOTS_GUARD:
-        if device.index not in _PIPES:
-            _PIPES[device.index] = _HostPipe(device)
-        return _PIPES[device.index]
-
-
-def streamed_chunk_rows(k: int, n: int, gs: int) -> int:
-    """Rows of W per pipeline chunk of ``rtn_quantize_streamed`` (a multiple of the group size), or 0
-    when the weight is not worth / not able to be chunked: chunks of 1/8 of the weight, at least
-    8 MB and at most one 32 MB staging chunk of f32 (codes: a quarter of that)."""
-    nbytes = 4 * k * n
-    if nbytes < _STREAM_MIN_BYTES or gs <= 0 or gs >= k or k % gs:
-        return 0
-    target = min(max(nbytes // 8, 8 << 20), dev._STAGE_CHUNK_ELEMS * 4)
-    rows = (target // (4 * n)) // gs * gs
-    if rows < gs or rows >= k:
-        return 0
-    return int(rows)
-
-
-def rtn_quantize_streamed(array: np.ndarray, quant_type, group_size: int, is_symmetric: bool,
-                          reduce_range: bool, clip_ratio: float):
-    """GROUP-strategy RTN (no MSE search) of one pageable host weight with the three legs of the
-    call overlapped INSIDE the call: while row chunk c goes up (host threads fill a pinned staging
-    chunk, DMA), chunk c-1 is quantized and chunk c-2's codes come down (DMA, host threads copy
-    them into the result array).  Groups never span chunks (chunk rows are a multiple of the group
-    size), so every chunk is an independent ``b200q_rtn_quantize`` on a (rows, N) slice; its
-    parameters are scattered into the reference's (N, G) order on the device.  The MSE search cannot
-    be chunked this way: its early stop is global over all rows (utils.py:232-237).
-
-    Returns raw ``(codes (K,N) uint8, scale (N*G,) f32, zp (N*G,) uint8)`` NumPy arrays, or None
-    when the weight does not qualify (small, ragged groups, not C-contiguous float32).
-    """
-    a = array
-    if not (isinstance(a, np.ndarray) and a.ndim == 2 and a.dtype == np.float32 and a.flags.c_contiguous):
-        return None
-    k, n = a.shape
-    gs = int(group_size)
-    rows = streamed_chunk_rows(k, n, gs)
-    if rows == 0:
-        return None
-    device = dev.require_cuda()
-    pipe = _host_pipe(device)
-    g_total, g_chunk = k // gs, rows // gs
-    chunks = [(r0, min(r0 + rows, k)) for r0 in range(0, k, rows)]
-    src = a.reshape(-1)
-    out_codes = np.empty((k, n), dtype=np.uint8)
-    out_flat = out_codes.reshape(-1)
-    compute = torch.cuda.current_stream(device)
-    with pipe.lock, dev._stage_lock:
-        up_bufs, up_views, up_evs = dev._staging(device)
-        wd = torch.empty((k, n), dtype=torch.float32, device=device)
-        codes_d = torch.empty((k, n), dtype=torch.uint8, device=device)
-        scale_d = torch.empty((n, g_total), dtype=torch.float32, device=device)
-        zp_d = torch.empty((n, g_total), dtype=torch.uint8, device=device)
-        sc_c = torch.empty((n * g_chunk,), dtype=torch.float32, device=device)
-        zp_c = torch.empty((n * g_chunk,), dtype=torch.uint8, device=device)
-        start = torch.cuda.Event()
-        start.record(compute)
-        pipe.h2d.wait_event(start)          # the fresh buffers may be recycled blocks of the compute stream
-        pipe.d2h.wait_event(start)
-        landed = [torch.cuda.Event() for _ in chunks]
-        done = [torch.cuda.Event() for _ in chunks]
-        for b in range(2):
-            up_evs[b].synchronize()
-            pipe.down_ev[b].synchronize()
-        for c in range(len(chunks) + 2):
-            futures = []
-            if c < len(chunks):
-                r0, r1 = chunks[c]
-                up_evs[c & 1].synchronize()                       # the DMA that last read this staging chunk
-                futures += dev.parallel_copy(up_views[c & 1][:(r1 - r0) * n], src[r0 * n:r1 * n])
-            if c >= 2:
-                r0, r1 = chunks[c - 2]
-                pipe.down_ev[c & 1].synchronize()                 # codes of chunk c-2 are in the pinned chunk
-                futures += dev.parallel_copy(out_flat[r0 * n:r1 * n], pipe.down_np[c & 1][:(r1 - r0) * n],
-                                             piece=4 << 20)
-            for f in futures:
-                f.result()
-            if c >= len(chunks):
-                continue
-            r0, r1 = chunks[c]
-            m = r1 - r0
-            with torch.cuda.stream(pipe.h2d):
-                wd[r0:r1].view(-1).copy_(up_bufs[c & 1][:m * n], non_blocking=True)
-                up_evs[c & 1].record(pipe.h2d)
-                landed[c].record(pipe.h2d)
-            compute.wait_event(landed[c])
-            gc = m // gs
-            sc_v, zp_v = (sc_c, zp_c) if gc == g_chunk else (sc_c[:n * gc], zp_c[:n * gc])
-            D.rtn_quantize(wd[r0:r1], quant_type, "group", gs, is_symmetric, reduce_range, clip_ratio, False,
-                           out=(codes_d[r0:r1], sc_v, zp_v))
-            g0 = r0 // gs
-            scale_d[:, g0:g0 + gc].copy_(sc_v.view(n, gc))
-            zp_d[:, g0:g0 + gc].copy_(zp_v.view(n, gc))
-            done[c].record(compute)
-            with torch.cuda.stream(pipe.d2h):
-                pipe.d2h.wait_event(done[c])
-                pipe.down[c & 1][:m * n].copy_(codes_d[r0:r1].view(-1), non_blocking=True)
-                pipe.down_ev[c & 1].record(pipe.d2h)
-        scale_np = scale_d.reshape(-1).cpu().numpy()
-        zp_np = zp_d.reshape(-1).cpu().numpy()
-    return out_codes, scale_np, zp_np

