@@ -187,7 +187,7 @@ def test_batched_stream_launch_matches_single_calls(cuda):
     job list (job table in kernel parameters); results must equal per-weight calls and the oracle."""
     from onnx_quantize_b200 import device_api as D
     rng = np.random.default_rng(21)
-    shapes = [(256, 128), (128, 48), (384, 1040 + 8), (1024, 256), (128, 16), (640, 4096)]
+    shapes = [(256, 128), (128, 48), (384, 1040 + 8), (1024, 256), (128, 16), (640, 4096), (1024, 8192), (2048, 1040)]
     ws = [torch.from_numpy((rng.standard_normal(s) * 0.02).astype(np.float32)).to(cuda) for s in shapes]
     for gs in (128, 32):
         outs = D.rtn_quantize_batch(ws, "uint4", "group", gs, False, False, 0.9, False, layout="matmul_nbits")

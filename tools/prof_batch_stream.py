@@ -16,3 +16,10 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 a.record(); plan.run(); b.record(); torch.cuda.synchronize()
 elts = sum(w.numel() for w in ws)
 print(f"{a.elapsed_time(b):.3f} ms, {elts*4.535/a.elapsed_time(b)/1e6:.0f} GB/s algorithmic")
+
+if os.environ.get("B200Q_PROF_NAMES"):
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        plan.run(); torch.cuda.synchronize()
+    for e in prof.key_averages():
+        print("  kernel:", e.key[:90], f"{e.device_time_total/1e3:.3f} ms x{e.count}")
