@@ -488,6 +488,9 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     if (fixup_ctl == nullptr && slab_quant_ok(W, m, kn_dst)) {
       dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kSlabCtaRows));
       quantize_slab_kernel<<<grid, 256, 0, st>>>(W, m, qs, out_scale, zp_rows, kn_dst);
+    } else if (fixup_ctl == nullptr && strategy != B200Q_TENSOR && ceil_div(K, kStatRowsPerCta) <= 65535) {
+      dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kStatRowsPerCta));
+      quantize_cols_kernel<<<grid, 128, 0, st>>>(W, m, qs, out_scale, zp_rows, kn_dst);
     } else {
       quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, st>>>(W, m, qs, out_scale, zp_rows,
                                                                     kn_dst, fixup_ctl);
@@ -648,6 +651,10 @@ int b200q_quantize_with_qparams(const float* W, int64_t K, int64_t N, int qtype,
   if (slab_quant_ok(W, s.map, out_codes)) {
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kSlabCtaRows));
     quantize_slab_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, s.map, qs, scale, (const unsigned char*)zp,
+                                                                 (unsigned char*)out_codes);
+  } else if (strategy != B200Q_TENSOR && ceil_div(K, kStatRowsPerCta) <= 65535) {
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(K, kStatRowsPerCta));
+    quantize_cols_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(W, s.map, qs, scale, (const unsigned char*)zp,
                                                                  (unsigned char*)out_codes);
   } else {
     quantize_rows_kernel<<<elementwise_grid(K * N), 256, 0, (cudaStream_t)stream>>>(

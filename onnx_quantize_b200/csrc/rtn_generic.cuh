@@ -29,33 +29,92 @@ struct RowMap {
   }
 };
 
-// ---- min/max per parameter row, column-segment strategies ---------------------------------
-// grid = (ceil(N/128), ceil(K/kRowsPerCta)); one thread per column walks its K-chunk and folds
-// into the order-preserving encoded min/max with one atomic pair per (column, group-in-chunk).
+// ---- min/max per parameter row, column-segment strategies, ANY shape --------------------------
+// grid = (ceil(N/128), ceil(K/kStatRowsPerCta)); one thread per column walks its K-chunk — eight
+// independent 4-byte loads in flight (a warp reads 128 contiguous bytes per row), group boundaries
+// tracked by a counter instead of a 64-bit division per row — and folds into the order-preserving
+// encoded min/max with one atomic pair per (column, group-in-chunk).  This is the route of ragged
+// shapes (N % 4 != 0, group sizes that are not multiples of 32); the first version (one load in
+// flight, a division per row) ran at 5-8 % of the HBM roofline.
 constexpr int kStatRowsPerCta = 256;
 
 static __global__ void __launch_bounds__(128) rowstats_cols_kernel(const float* __restrict__ W, RowMap m,
                                                             unsigned int* __restrict__ enc_min,
                                                             unsigned int* __restrict__ enc_max) {
-  int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (n >= m.N) return;
-  int64_t k0 = (int64_t)blockIdx.y * kStatRowsPerCta;
-  int64_t k1 = min(k0 + (int64_t)kStatRowsPerCta, m.K);
+  const int64_t k0 = (int64_t)blockIdx.y * kStatRowsPerCta;
+  const int64_t k1 = min(k0 + (int64_t)kStatRowsPerCta, m.K);
   float mn = INFINITY, mx = -INFINITY;
   int64_t g = k0 / m.gs;
-  for (int64_t k = k0; k < k1; ++k) {
-    int64_t gk = k / m.gs;
-    if (gk != g) {
-      atomicMin(&enc_min[n * m.G + g], float_to_ordered(mn));
-      atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
-      mn = INFINITY; mx = -INFINITY; g = gk;
+  int64_t boundary = (g + 1) * m.gs;           // first row of the next group
+  const float* col = W + n;
+  for (int64_t k = k0; k < k1; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = k + u < k1 ? __ldg(col + (k + u) * m.N) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (k + u < k1) {
+        if (k + u == boundary) {
+          atomicMin(&enc_min[n * m.G + g], float_to_ordered(mn));
+          atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
+          mn = INFINITY; mx = -INFINITY; ++g; boundary += m.gs;
+        }
+        mn = fminf(mn, v[u]);
+        mx = fmaxf(mx, v[u]);
+      }
     }
-    float v = __ldg(&W[k * m.N + n]);
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
   }
   atomicMin(&enc_min[n * m.G + g], float_to_ordered(mn));
   atomicMax(&enc_max[n * m.G + g], float_to_ordered(mx));
+}
+
+// A4 with given per-row parameters for ANY shape (column-segment strategies), KN_BYTES output: same
+// mapping as rowstats_cols_kernel; the row's parameters are reloaded at group boundaries only and
+// the codes come from the validated reciprocal product (see rtn_stream.cuh), redone with the IEEE
+// division when a rounding tie cannot be excluded.
+static __global__ void __launch_bounds__(128) quantize_cols_kernel(
+    const float* __restrict__ W, RowMap m, QSpec qs, const float* __restrict__ scale,
+    const unsigned char* __restrict__ zp, unsigned char* __restrict__ out) {
+  const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (n >= m.N) return;
+  const int64_t k0 = (int64_t)blockIdx.y * kStatRowsPerCta;
+  const int64_t k1 = min(k0 + (int64_t)kStatRowsPerCta, m.K);
+  constexpr float kMagic = 12582912.0f;
+  const float delta = qs.bits == 4 ? 1.9073486328125e-06f : 3.0517578125e-05f;   // 2^-19 / 2^-15
+  const float u_lo = kMagic + (float)qs.qmin, u_hi = kMagic + (float)qs.qmax;
+  int64_t g = k0 / m.gs;
+  int64_t boundary = (g + 1) * m.gs;
+  float sc, inv, cc, thr;
+  int z;
+  auto load_params = [&](int64_t gg) {
+    const int64_t r = n * m.G + gg;
+    sc = scale[r];
+    z = decode_code(zp[r], qs);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sc));
+    cc = kMagic + (float)z;
+    thr = sc * (0.5f - delta);
+  };
+  load_params(g);
+  const float* col = W + n;
+  unsigned char* dst = out + n;
+  for (int64_t k = k0; k < k1; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = k + u < k1 ? __ldg(col + (k + u) * m.N) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (k + u < k1) {
+        if (k + u == boundary) { ++g; boundary += m.gs; load_params(g); }
+        const float t = __fadd_rn(__fmul_rn(v[u], inv), cc);
+        const float e = __fmaf_rn(__fadd_rn(t, -cc), -sc, v[u]);
+        unsigned int q = __float_as_uint(fminf(fmaxf(t, u_lo), u_hi));
+        if (!(fabsf(e) < thr)) q = (unsigned int)quant_code(v[u], sc, z, qs.qmin, qs.qmax);
+        dst[(k + u) * m.N] = (unsigned char)(qs.bits == 4 ? (q & 0xFu) : (q & 0xFFu));
+      }
+    }
+  }
 }
 
 // ---- tuned variants for N % 4 == 0, 16-byte aligned W and groups that are multiples of 32 rows.
