@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "minmax.cuh"
+#include "mse_channel.cuh"
 #include "mse_generic.cuh"
 #include "rtn_fused.cuh"
 #include "rtn_generic.cuh"
@@ -72,10 +73,15 @@ struct RtnWorkspace {
   unsigned char* codes_tmp;
   float* tensor_sums;      // TENSOR + MSE: [20][2][n_blocks] block sums of the parallel pairwise summation
   int* tile_counter;       // the streaming ring kernel's tile dispenser (zeroed before the launch)
+  float* ch_part;          // CHANNEL + MSE: [slabs][20][N] tier-1 partial sums (mse_channel.cuh)
+  float* ch_approx;        //                [20][N] tier-1 scores
+  unsigned int* ch_need;   //                [N] pairs tier 2 evaluates (bit mask per column)
+  unsigned int* ch_list;   //                compact list of those pairs, ch_list[20 * N] = their number
   size_t total;
 };
 
-static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool mse, bool tensor = false) {
+static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool mse, bool tensor = false,
+                          bool channel = false) {
   RtnWorkspace w;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -100,6 +106,11 @@ static RtnWorkspace carve(void* base, int64_t rows, int64_t K, int64_t N, bool m
                            (size_t)2 * kPwMaxNodes + 256;
     w.tensor_sums = (float*)take(mse && tensor ? (perfect > general ? perfect : general) : 0);
   }
+  const bool ch = mse && channel;
+  w.ch_part = (float*)take(ch ? (size_t)ceil_div(K, kChSlabRows) * kMseCandidates * N * 4 : 0);
+  w.ch_approx = (float*)take(ch ? (size_t)kMseCandidates * N * 4 : 0);
+  w.ch_need = (unsigned int*)take(ch ? (size_t)N * 4 : 0);
+  w.ch_list = (unsigned int*)take(ch ? ((size_t)N * kMseCandidates + 1) * 4 : 0);
   w.total = off;
   return w;
 }
@@ -306,6 +317,44 @@ static int launch_mse_error_table(const float* W, const RowMap& m, const QSpec& 
   return B200Q_OK;
 }
 
+// CHANNEL + MSE in two tiers (mse_channel.cuh): columns summed sequentially down K (N > 1)
+static bool channel_two_tier_ok(const RowMap& m) {
+  return m.strategy == B200Q_CHANNEL && m.G == 1 && m.N >= 32 && m.N < (1ll << 26) && m.K >= 64 &&
+         ceil_div(m.K, kChSlabRows) <= 65535;
+}
+
+static int launch_mse_channel_masks(const float* W, const RowMap& m, const QSpec& qs, const RtnWorkspace& ws,
+                                    cudaStream_t st) {
+  const int n_slabs = (int)ceil_div(m.K, kChSlabRows);
+  dim3 grid((unsigned)ceil_div(m.N, 32), (unsigned)n_slabs);
+  mse_channel_approx_kernel<<<grid, dim3(32, kMseCandidates / kChCandPerThread), 0, st>>>(
+      W, m.K, m.N, qs, ws.enc_min, ws.enc_max, ws.ch_part);
+  B200Q_LAUNCH_OK();
+  const unsigned cblocks = (unsigned)ceil_div(m.N, 128);
+  unsigned int* count = ws.ch_list + (size_t)m.N * kMseCandidates;
+  B200Q_CUDA_OK(cudaMemsetAsync(count, 0, 4, st));
+  mse_channel_classify_kernel<<<cblocks, 128, 0, st>>>(ws.ch_part, n_slabs, m.N, m.K, ws.enc_min, ws.enc_max,
+                                                       ws.ch_approx, ws.ch_need, ws.ch_list, count);
+  B200Q_LAUNCH_OK();
+  mse_channel_exact_kernel<<<kNumSMs * 8, 256, 0, st>>>(W, m.K, m.N, qs, ws.enc_min, ws.enc_max, ws.ch_list, count,
+                                                         ws.err);
+  B200Q_LAUNCH_OK();
+  mse_channel_masks_kernel<<<cblocks, 128, 0, st>>>(ws.ch_approx, ws.err, ws.ch_need, m.N, m.K, ws.masks, ws.ctl);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
+// per-row improvement masks (ws.masks) and their OR (ws.ctl->or_mask) of the MSE search
+static int launch_mse_masks(const float* W, const RowMap& m, int64_t rows, const QSpec& qs, const RtnWorkspace& ws,
+                            cudaStream_t st) {
+  if (channel_two_tier_ok(m) && ws.ch_part != nullptr) return launch_mse_channel_masks(W, m, qs, ws, st);
+  const int erc = launch_mse_error_table(W, m, qs, ws, ws.err, st);
+  if (erc != B200Q_OK) return erc;
+  mse_row_masks_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(ws.err, rows, ws.masks, ws.ctl);
+  B200Q_LAUNCH_OK();
+  return B200Q_OK;
+}
+
 int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, int64_t group_size,
                  int symmetric, int reduce_range, double clip_ratio, int mse, float* out_scale,
                  unsigned char* out_zp, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -315,7 +364,7 @@ int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, 
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR, strategy == B200Q_CHANNEL);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   rc = launch_rowstats(W, s.map, s.rows, ws, st);
@@ -323,9 +372,7 @@ int rows_qparams(const float* W, int64_t K, int64_t N, int qtype, int strategy, 
   const int blocks = (int)ceil_div(s.rows, 256);
   if (mse) {
     B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
-    { const int erc = launch_mse_error_table(W, s.map, qs, ws, ws.err, st); if (erc != B200Q_OK) return erc; }
-    mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
-    B200Q_LAUNCH_OK();
+    { const int erc = launch_mse_masks(W, s.map, s.rows, qs, ws, st); if (erc != B200Q_OK) return erc; }
     mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows, qs,
                                                 out_scale, out_zp, nullptr, kFinalizeGeneric);
   } else {
@@ -345,7 +392,7 @@ extern "C" {
 size_t b200q_rtn_workspace_bytes(int64_t K, int64_t N, int strategy, int64_t group_size, int mse) {
   Shape s;
   if (resolve_shape(K, N, strategy, group_size, &s) != B200Q_OK) return 0;
-  return carve(nullptr, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR).total;
+  return carve(nullptr, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR, strategy == B200Q_CHANNEL).total;
 }
 
 int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int strategy,
@@ -373,7 +420,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     B200Q_REQUIRE(m.gs >= 16 && (m.gs & (m.gs - 1)) == 0, B200Q_ERR_INVALID_ARG,
                   "MATMUL_NBITS needs a power-of-two group size >= 16 (got %lld)", (long long)m.gs);
   }
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR, strategy == B200Q_CHANNEL);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   B200Q_REQUIRE(clip_ratio > 0.0 && clip_ratio <= 1.0, B200Q_ERR_INVALID_ARG,
@@ -470,9 +517,7 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
     rc = launch_rowstats(W, m, s.rows, ws, st);
     if (rc != B200Q_OK) return rc;
     if (mse) {
-      { const int erc = launch_mse_error_table(W, m, qs, ws, ws.err, st); if (erc != B200Q_OK) return erc; }
-      mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
-      B200Q_LAUNCH_OK();
+      { const int erc = launch_mse_masks(W, m, s.rows, qs, ws, st); if (erc != B200Q_OK) return erc; }
       mse_finalize_kernel<<<blocks, 256, 0, st>>>(ws.masks, ws.ctl, ws.enc_min, ws.enc_max, s.rows,
                                                   qs, out_scale, zp_rows, out_mse_info,
                                                   kFinalizeGeneric);
@@ -598,7 +643,7 @@ int b200q_mse_error_table(const float* W, int64_t K, int64_t N, int qtype, int s
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, true, strategy == B200Q_TENSOR);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, true, strategy == B200Q_TENSOR, strategy == B200Q_CHANNEL);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   rc = launch_rowstats(W, s.map, s.rows, ws, st);
@@ -619,7 +664,7 @@ int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strate
   Shape s;
   int rc = resolve_shape(K, N, strategy, group_size, &s);
   if (rc != B200Q_OK) return rc;
-  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR);
+  RtnWorkspace ws = carve(workspace, s.rows, K, N, mse != 0, strategy == B200Q_TENSOR, strategy == B200Q_CHANNEL);
   B200Q_REQUIRE(workspace && workspace_bytes >= ws.total, B200Q_ERR_WORKSPACE,
                 "workspace of %zu bytes needed, %zu given", ws.total, workspace_bytes);
   rc = launch_rowstats(W, s.map, s.rows, ws, st);
@@ -627,9 +672,7 @@ int b200q_row_ranges(const float* W, int64_t K, int64_t N, int qtype, int strate
   int blocks = (int)ceil_div(s.rows, 256);
   if (mse) {
     B200Q_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(MseControl), st));
-    { const int erc = launch_mse_error_table(W, s.map, qs, ws, ws.err, st); if (erc != B200Q_OK) return erc; }
-    mse_row_masks_kernel<<<blocks, 256, 0, st>>>(ws.err, s.rows, ws.masks, ws.ctl);
-    B200Q_LAUNCH_OK();
+    { const int erc = launch_mse_masks(W, s.map, s.rows, qs, ws, st); if (erc != B200Q_OK) return erc; }
   }
   row_ranges_kernel<<<blocks, 256, 0, st>>>(ws.enc_min, ws.enc_max, mse ? ws.masks : nullptr,
                                             ws.ctl, s.rows, (float)clip_ratio, out_min, out_max);

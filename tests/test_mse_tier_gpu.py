@@ -81,3 +81,60 @@ def test_two_tier_adversarial_ties(cuda):
         qo, so, zo = O.rtn_quantize(w, qt, "group", 128, sym, False, 1.0, True)
         assert np.array_equal(bits(s.cpu().numpy()), bits(so.reshape(-1))), qt
         assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8)), qt
+
+
+# ---- CHANNEL strategy: two tiers over sequentially summed columns (csrc/mse_channel.cuh) ------------
+@pytest.mark.parametrize("qt,sym,shape", [("int8", True, (1024, 160)), ("uint8", False, (4096, 64)),
+                                          ("int4", True, (2048, 96)), ("uint4", False, (512, 320)),
+                                          ("int8", False, (200, 33))])
+def test_channel_two_tier_matches_oracle(cuda, qt, sym, shape):
+    """Codes, scales and zero points of CHANNEL + MSE equal the oracle's (every candidate exact, NumPy's
+    sequential order down the F-ordered column view) although only the pairs the interval
+    classification could not decide are evaluated exactly."""
+    rng = np.random.default_rng(stable_seed(qt, sym, shape))
+    w = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    w[rng.integers(0, shape[0], 40), rng.integers(0, shape[1], 40)] *= 15       # outliers: later optimum
+    w[:, 3] = 0.0                                                                # all-zero column
+    w[:, 5] *= np.float32(1e-15)                                                 # below the approximation's floor
+    w[:, 7] = np.float32(0.25)                                                   # constant column
+    wt = torch.from_numpy(w).to(cuda)
+    q, s, z, info = D.rtn_quantize(wt, qt, "channel", -1, sym, False, 1.0, True, return_info=True)
+    qo, so, zo = O.rtn_quantize(w, qt, "channel", -1, sym, False, 1.0, True)
+    _, _, trace = O.mse_min_max(O.to_rows(w, "channel"), qt, "channel", sym, False, return_trace=True)
+    assert int(info[0]) == len(trace) - 1                                        # same early-stop step
+    assert np.array_equal(bits(s.cpu().numpy()), bits(np.asarray(so).reshape(-1)))
+    assert np.array_equal(z.cpu().numpy(), np.asarray(zo).reshape(-1).view(np.uint8))
+    assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8))
+
+
+def test_channel_two_tier_equals_all_exact_at_4096(cuda):
+    """4096 x 4096 int8 / int4 per-channel with the search: the error table API evaluates all 20 x N pairs
+    exactly (the round-1 route); the improvement masks derived from it must give the parameters the
+    two-tier route returns."""
+    g = torch.Generator(device=cuda)
+    g.manual_seed(77)
+    w = torch.randn((4096, 4096), device=cuda, generator=g) * 0.02
+    for qt, sym in (("int8", True), ("int4", True), ("uint4", False)):
+        _, s, z = D.rtn_quantize(w, qt, "channel", -1, sym, False, 1.0, True)
+        err = D.mse_error_table(w, qt, "channel", -1, sym, False)                # (20, N) exact sums
+        e = err.cpu().numpy()
+        best = np.full(e.shape[1], np.inf, np.float32)
+        masks = np.zeros(e.shape[1], np.uint32)
+        for i in range(20):
+            imp = e[i] < best
+            best = np.where(imp, e[i], best)
+            masks |= imp.astype(np.uint32) << np.uint32(i)
+        stalls, stop = 0, 19
+        any_imp = [bool(((masks >> np.uint32(i)) & 1).any()) for i in range(20)]
+        for i in range(20):
+            stalls += 0 if any_imp[i] else 1
+            if stalls >= 5:
+                stop = i
+                break
+        masks &= np.uint32((2 << stop) - 1)
+        best_i = np.where(masks != 0, np.floor(np.log2(np.maximum(masks, 1))).astype(np.int64), 0)
+        lo, hi = D.row_ranges(w, qt, "channel", -1, sym, False, 1.0, mse=False)
+        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        p = (1.0 - best_i / 100.0).astype(np.float32)
+        so, zo = O.qparams(p * np.minimum(lo, 0), p * np.maximum(hi, 0), qt, sym, False)
+        assert np.array_equal(bits(s.cpu().numpy()), bits(np.asarray(so).reshape(-1))), qt
