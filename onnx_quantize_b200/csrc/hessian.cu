@@ -449,6 +449,246 @@ hessian_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap, const HessianPar
   }
 }
 
+// =================================================================================================
+// BF16x3 on CTA PAIRS (tcgen05 cta_group::2).  The one-CTA kernel above lands 96 KB of operands per
+// 64-token stage and SM (A 128 rows + B 256 rows, two planes) for 12 MMAs of 128 x 256 x 16: at the
+// full MMA rate that is ~9.2 KB per clock over the chip, more than the L2 -> SM fabric delivers
+// (ncu: tensor pipe 84 % on a pure MMA chunk, 76 % with the fused split).  A pair of SMs computes a
+// 256 x 256 tile instead: each CTA stages ITS 128 rows of A and ITS 128 rows (half) of B — 64 KB per
+// stage and SM for the same number of MMA cycles — and holds the 128 x 256 half of the accumulator
+// that belongs to its rows in its own TMEM.  The leader CTA (cluster rank 0) issues every MMA.
+//   full[s]       own TMA bytes landed                           (per CTA, count 1 + tx)
+//   peer_full[s]  leader only: the peer's stage s has landed     (remote arrive by the peer's warp 1)
+//   empty[s]      both CTAs: the MMAs that read stage s retired  (tcgen05.commit, multicast)
+//   tmem_full[a]  both CTAs: accumulator a complete              (tcgen05.commit, multicast)
+//   tmem_empty[a] leader only: both epilogues drained a          (128 local + 128 remote arrivals)
+// =================================================================================================
+constexpr int kPairTile = 256;                              // rows and columns of H per CTA pair and unit
+constexpr int kPairPlaneBytes = kTileM * kBfTT * 2;         // 16 KB: 128 channels x 64 tokens of one plane
+constexpr int kPairStageBytes = 4 * kPairPlaneBytes;        // A1, B1, A2, B2: 64 KB per CTA
+constexpr int kPairStages = 3;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+// unit -> (tile row ib, tile column jb >= ib, token split): 256 x 256 tiles of the upper triangle
+__device__ __forceinline__ void decode_pair_unit(int n_b, int n_tiles, int unit, int& ib, int& jb, int& sp) {
+  sp = unit / n_tiles;
+  int tile = unit - sp * n_tiles;
+  for (ib = 0; ib < n_b; ++ib) {
+    const int cnt = n_b - ib;
+    if (tile < cnt) { jb = ib + tile; return; }
+    tile -= cnt;
+  }
+  ib = 0; jb = 0;
+}
+
+// p.n_ib = number of 256-blocks, p.n_tiles = n_ib (n_ib + 1) / 2, p.T = padded tokens of this chunk
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBfThreads, 1)
+hessian_bf16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const HessianParams p, const SplitJob next) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kPairStages * kPairStageBytes);
+  uint64_t* peer_full = full_bar + kPairStages;
+  uint64_t* empty_bar = peer_full + kPairStages;
+  uint64_t* tmem_full = empty_bar + kPairStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+  uint32_t* split_words = (uint32_t*)(smem + kPairStages * kPairStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_units = p.n_tiles * p.splits;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&peer_full[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();            // the peer's barriers are initialised before anybody signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): A1, B1, A2, B2 of THIS CTA's halves =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = pair; unit < n_units; unit += n_pairs) {
+        int ib, jb, sp;
+        decode_pair_unit(p.n_ib, p.n_tiles, unit, ib, jb, sp);
+        const int64_t t0 = (int64_t)sp * p.t_per_split;
+        const int64_t t1 = min(t0 + p.t_per_split, p.T);
+        const int row_a = ib * kPairTile + (int)rank * kTileM, row_b = jb * kPairTile + (int)rank * kTileM;
+        for (int64_t t = t0; t < t1; t += kBfTT) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sb = smem + stage * kPairStageBytes;
+          mbar_expect_tx(&full_bar[stage], kPairStageBytes);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            tma_load_3d(sb + (2 * pl) * kPairPlaneBytes, &tmap, &full_bar[stage], (int)t, row_a, pl);
+            tma_load_3d(sb + (2 * pl + 1) * kPairPlaneBytes, &tmap, &full_bar[stage], (int)t, row_b, pl);
+          }
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (!leader) {
+        // ===== peer: tell the leader when a stage of THIS CTA has landed =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = pair; unit < n_units; unit += n_pairs) {
+          int ib, jb, sp;
+          decode_pair_unit(p.n_ib, p.n_tiles, unit, ib, jb, sp);
+          const int64_t t0 = (int64_t)sp * p.t_per_split;
+          const int64_t t1 = min(t0 + p.t_per_split, p.T);
+          for (int64_t t = t0; t < t1; t += kBfTT) {
+            mbar_wait(&full_bar[stage], phase);
+            mbar_arrive_remote(map_to_rank(&peer_full[stage], 0));
+            if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        // ===== leader: MMA issuer for the pair =====
+        constexpr uint32_t idesc = umma_idesc_bf16(kPairTile, kPairTile);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int unit = pair; unit < n_units; unit += n_pairs) {
+          int ib, jb, sp;
+          decode_pair_unit(p.n_ib, p.n_tiles, unit, ib, jb, sp);
+          const int64_t t0 = (int64_t)sp * p.t_per_split;
+          const int64_t t1 = min(t0 + p.t_per_split, p.T);
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d = tmem_base + (uint32_t)acc * kPairTile;
+          uint32_t accumulate = 0;
+          for (int64_t t = t0; t < t1; t += kBfTT) {
+            mbar_wait(&full_bar[stage], phase);
+            mbar_wait(&peer_full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a1 = smem_u32(smem + stage * kPairStageBytes), b1 = a1 + kPairPlaneBytes;
+            const uint32_t a2 = a1 + 2 * kPairPlaneBytes, b2 = a1 + 3 * kPairPlaneBytes;
+#pragma unroll
+            for (int k = 0; k < kBfTT / 16; ++k) {
+              const uint64_t da1 = umma_desc_k_sw128(a1 + k * 32), db1 = umma_desc_k_sw128(b1 + k * 32);
+              const uint64_t da2 = umma_desc_k_sw128(a2 + k * 32), db2 = umma_desc_k_sw128(b2 + k * 32);
+              umma_bf16_pair(d, da1, db1, idesc, accumulate);
+              accumulate = 1;
+              umma_bf16_pair(d, da1, db2, idesc, 1);
+              umma_bf16_pair(d, da2, db1, idesc, 1);
+            }
+            umma_commit_pair(&empty_bar[stage]);
+            if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue (both CTAs): this CTA's 128 rows of the 256 x 256 tile =====
+    const int q = warp & 3;
+    const uint32_t leader_empty[2] = {map_to_rank(&tmem_empty[0], 0), map_to_rank(&tmem_empty[1], 0)};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = pair; unit < n_units; unit += n_pairs) {
+      int ib, jb, sp;
+      decode_pair_unit(p.n_ib, p.n_tiles, unit, ib, jb, sp);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t i = (int64_t)ib * kPairTile + rank * kTileM + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kPairTile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kPairTile + c0), r);
+        const int64_t j0 = (int64_t)jb * kPairTile + c0;
+        if (i < p.K && j0 < p.K && j0 + 31 >= i) {   // K % 32 == 0: a 32-column run is all in or all out
+          float* dst = p.H + i * p.K + j0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float v0 = p.alpha * __uint_as_float(r[c]), v1 = p.alpha * __uint_as_float(r[c + 1]);
+            const float v2 = p.alpha * __uint_as_float(r[c + 2]), v3 = p.alpha * __uint_as_float(r[c + 3]);
+            if (j0 + c >= i) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v0), "f"(v1),
+                           "f"(v2), "f"(v3)
+                           : "memory");
+            } else if (j0 + c + 3 >= i) {
+              if (j0 + c + 1 >= i) atomicAdd(dst + c + 1, v1);
+              if (j0 + c + 2 >= i) atomicAdd(dst + c + 2, v2);
+              atomicAdd(dst + c + 3, v3);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive_remote(leader_empty[acc]);          // the leader's own threads arrive through the same path
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    split_tiles(next, split_words, blockIdx.x, gridDim.x, threadIdx.x - 256);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();            // nobody leaves while the peer may still signal its barriers or read its operands
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
 // H[j][i] <- H[i][j] for j > i: the contraction only accumulates the upper triangle, so the result
 // is exactly symmetric whatever order the split-token partial sums arrived in.
 __global__ void mirror_upper_kernel(float* __restrict__ H, int64_t K) {
@@ -585,6 +825,17 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
     const size_t smem = (size_t)kBfStages * kBfStageBytes + 1024 + 256 + kSplitSmemBytes;
     B200Q_CUDA_OK(cudaFuncSetAttribute(hessian_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
+    const size_t pair_smem = (size_t)kPairStages * kPairStageBytes + 1024 + 256 + kSplitSmemBytes;
+    B200Q_CUDA_OK(cudaFuncSetAttribute(hessian_bf16x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pair_smem));
+    // CTA pairs or single CTAs?  Measured on B200, T = 32768, time of pairs / time of single CTAs
+    // (tools/prof_hessian_ab.py): K = 1024 0.98, 2048 0.98, 3072 0.98, 4096 0.97, 5120 1.00, 6912 1.05,
+    // 8192 1.09, 11008 0.94, 14336 0.98.  The pairs stage a third fewer operand bytes per MMA cycle,
+    // but the kernel is not bound by that fabric (single CTAs already issue 1.20 PFLOP/s of bf16 MMAs at
+    // K = 4096, 86 % of the sustained cuBLAS rate); for 5000 < K < 10000 the pairs' coarser tile walk
+    // loses L2 locality on the planes.  B200Q_HESSIAN_PAIRS=0/1 forces either kernel.
+    bool use_pairs = K <= 5000 || K >= 10000;
+    if (const char* e = getenv("B200Q_HESSIAN_PAIRS")) use_pairs = e[0] == '1';
     auto job = [&](int64_t c0, int buf) {
       SplitJob j;
       j.X = nullptr; j.tc = 0; j.tc_pad = 0; j.K = K; j.planes = nullptr;
@@ -633,6 +884,22 @@ int b200q_hessian_accumulate(const float* X, int64_t T, int64_t K, float alpha, 
       q.T = tc_pad;
       q.t_per_split = chunk_stages * kBfTT;
       q.splits = (int)ceil_div(tc_pad, q.t_per_split);
+      if (use_pairs) {
+        q.n_ib = (int)ceil_div(K, kPairTile);
+        q.n_jb = q.n_ib;
+        q.n_tiles = q.n_ib * (q.n_ib + 1) / 2;
+        const int n_units = q.n_tiles * q.splits;
+        int pairs = kNumSMs / 2;
+        if (next.X == nullptr && n_units < pairs) pairs = n_units;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(kBfThreads);
+        cfg.dynamicSmemBytes = pair_smem;
+        cfg.stream = st;
+        B200Q_CUDA_OK(cudaLaunchKernelEx(&cfg, hessian_bf16x3_pair_kernel, bmap, q, next));
+        count_launch();
+        continue;
+      }
       const int n_units = q.n_tiles * q.splits;
       // with a chunk to convert every SM gets a CTA even when there are fewer MMA units than SMs
       const int grid = (next.X != nullptr || n_units >= kNumSMs) ? kNumSMs : n_units;

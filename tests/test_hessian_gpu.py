@@ -49,3 +49,23 @@ def test_streaming_accumulator_matches_oracle(cuda):
     assert acc.num_samples == n
     got = acc.h.cpu().numpy()
     assert np.abs(got - h).max() / np.abs(h).max() < 2e-5
+
+
+@pytest.mark.parametrize("pairs", ["0", "1"])
+@pytest.mark.parametrize("t,k", [(4096, 512), (3000, 1152), (8192, 6912), (2048, 96), (5000, 800)])
+def test_bf16x3_single_cta_and_cta_pair_kernels(cuda, monkeypatch, pairs, t, k):
+    """Both tcgen05 kernels of the BF16x3 mode — 128 x 256 tiles on one CTA (cta_group::1) and
+    256 x 256 tiles on a CTA pair (cta_group::2, each CTA staging its half of both operands) — against
+    float64, whatever the size heuristic would pick; ragged K (not a multiple of 256) and T."""
+    monkeypatch.setenv("B200Q_HESSIAN_PAIRS", pairs)
+    g = torch.Generator(device=cuda)
+    g.manual_seed(t + k)
+    x = torch.randn((t, k), device=cuda, generator=g)
+    x[:, 7] = 0
+    h = torch.full((k, k), 0.25, device=cuda)
+    hessian_accumulate(x, h, alpha=2.0 / 16, beta=1.0, precision="bf16x3")
+    want = _ref(x, 2.0 / 16) + 0.25
+    err = ((h.double() - want).abs().max() / want.abs().max()).item()
+    assert err < TOL["bf16x3"], err
+    assert torch.equal(h, h.T)
+    assert torch.all(h[7, :] == 0.25)
