@@ -34,25 +34,55 @@ class _TensorState:
 
 
 class _LazyData(dict):
-    """``calibrator.data``: name → CalibrationData, materialised from the device on access."""
+    """``calibrator.data``: name → CalibrationData, materialised from the device on EVERY read access
+    (item, ``get``, iteration over values / items, ``copy``, ``dict(data)``, pickling), so that a
+    reader never sees the placeholder of a pending batch; entries written directly by the user (the
+    reference's ``.data`` is a plain dict) stay as they are."""
 
     def __init__(self, owner: "MinMaxCalibrator"):
         super().__init__()
         self._owner = owner
 
+    def _sync_all(self) -> None:
+        for name in list(dict.keys(self)):
+            self._owner._sync(name)
+
     def __getitem__(self, name):
         self._owner._sync(name)
         return super().__getitem__(name)
 
+    def get(self, name, default=None):
+        if dict.__contains__(self, name):
+            return self[name]
+        return default
+
+    def setdefault(self, name, default=None):
+        if dict.__contains__(self, name):
+            return self[name]
+        return super().setdefault(name, default)
+
+    def pop(self, name, *default):
+        self._owner._sync(name)
+        return super().pop(name, *default)
+
     def values(self):
-        for name in list(self):
-            self._owner._sync(name)
+        self._sync_all()
         return super().values()
 
     def items(self):
-        for name in list(self):
-            self._owner._sync(name)
+        self._sync_all()
         return super().items()
+
+    def copy(self) -> dict:
+        self._sync_all()
+        return dict(dict.items(self))
+
+    def __iter__(self):                  # also takes dict(data) / {**data} off CPython's raw-copy fast path
+        self._sync_all()
+        return super().__iter__()
+
+    def __reduce__(self):                # pickles as the plain dict the reference holds
+        return (dict, (self.copy(),))
 
 
 class MinMaxCalibrator(Calibrator):
@@ -111,7 +141,7 @@ class MinMaxCalibrator(Calibrator):
 
     def compute_range(self, name: str) -> tuple[np.ndarray, np.ndarray]:
         """(min, max) with zero included, as 0-d float32 arrays (reference minmax.py:66-87)."""
-        if name not in self._dev:
+        if name not in self._dev and not dict.__contains__(self.data, name):   # .data may be filled directly
             raise KeyError(f"No calibration data collected for '{name}'")
         d = self.data[name]
         return (np.array(np.minimum(d.min_val, 0), dtype=np.float32),

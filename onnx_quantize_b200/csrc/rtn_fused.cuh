@@ -75,6 +75,12 @@ enum FusedMode { kPlain = 0, kExact = 1, kTwoTier = 2 };
 // 16) — 8-bit types keep the IEEE division so no flip exists —, the reference's own np.power /
 // pairwise-sum rounding 5e-7.  delta <= 1.7e-5, tau = 4e-5 > 2 delta / (1 - delta) = 3.4e-5.
 constexpr float kTierTau = 4.0e-5f;
+// The budget above holds for |d| >= 1e-12, i.e. terms >= 1.6e-29.  A group whose best approximate
+// score is below kTierFloor has terms outside that range (2.4 * lg2|d| near -127, results flushed by
+// ex2.approx.ftz while NumPy keeps denormals): none of its tier-1 conclusions is used — every
+// candidate is re-evaluated exactly, nothing counts as proven, everything as possible.  (An all-zero
+// group has exactly zero errors in the reference as well and needs no such treatment.)
+constexpr float kTierFloor = 1.0e-26f;
 
 struct FusedArgs {
   const float* W;
@@ -377,6 +383,11 @@ rtn_group_fused_kernel(const __grid_constant__ FusedArgs a) {
       pick[c] = i1;
       // ambiguous (or non-finite scores): the two best if the third is out of reach, else all
       redo[c] = (s2 > limit) ? 0u : ((s3 > limit) ? ((1u << i1) | (1u << i2)) : ((1u << n_cand) - 1u));
+      if (s1 < kTierFloor && hi0 - lo0 > 0.0f) {   // below the range the error budget was established on
+        redo[c] = (1u << n_cand) - 1u;
+        proven = 0u;
+        possible = (1u << n_cand) - 1u;
+      }
       proven_any |= proven;
       possible_any |= possible;
     }

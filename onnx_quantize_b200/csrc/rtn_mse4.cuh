@@ -161,6 +161,11 @@ rtn_group_mse4_kernel(const __grid_constant__ FusedArgs a) {
     pick[c] = i1[c];
     // ambiguous (or non-finite scores): the two best if the third is out of reach, else all
     redo[c] = (s2[c] > limit) ? 0u : ((s3[c] > limit) ? ((1u << i1[c]) | (1u << i2[c])) : ((1u << n_cand) - 1u));
+    if (s1[c] < kTierFloor && hi0[c] - lo0[c] > 0.0f) {   // below the range the error budget was established on (rtn_fused.cuh)
+      redo[c] = (1u << n_cand) - 1u;
+      proven[c] = 0u;
+      possible[c] = (1u << n_cand) - 1u;
+    }
     proven_any |= proven[c];
     possible_any |= possible[c];
   }

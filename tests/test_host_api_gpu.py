@@ -309,3 +309,30 @@ def test_bulk_pipeline_with_pageable_weights(cuda):
                                     np.dtype(np.float32), q.QuantType.QUInt4.np_dtype)
         assert np.array_equal(c.reshape(w.shape), qc.astype(np.uint8))
         assert np.array_equal(s.reshape(-1).view(np.uint32), qs_.reshape(-1).view(np.uint32))
+
+
+def test_calibrator_data_is_materialised_on_every_kind_of_read(cuda):
+    """`.data` of the reference is a plain dict of real numbers; here it is filled lazily from the
+    device, so every read path has to trigger the fold: get, copy, dict(), iteration, pickling — and
+    entries a caller writes directly (the reference allows it) must work in compute_range."""
+    import pickle
+
+    from onnx_quantize_b200.core._calibration.base import CalibrationData
+    from onnx_quantize_b200.core._calibration.minmax import MinMaxCalibrator
+    c = MinMaxCalibrator()
+    c.collect("a", np.array([[-2.0, 3.0]], np.float32))
+    assert c.data.get("a").max_val == 3.0
+    c.collect("a", np.array([[5.0]], np.float32))                    # pending again
+    assert dict(c.data)["a"].max_val == 5.0
+    c.collect("a", np.array([[7.0]], np.float32))
+    assert c.data.copy()["a"].max_val == 7.0
+    c.collect("a", np.array([[9.0]], np.float32))
+    assert [v.max_val for v in c.data.values()] == [9.0]
+    c.collect("a", np.array([[-11.0]], np.float32))
+    assert pickle.loads(pickle.dumps(c.data))["a"].min_val == -11.0
+    assert c.data.get("missing") is None and c.data.setdefault("a").min_val == -11.0
+    c.data["manual"] = CalibrationData(np.float32(0.5), np.float32(2.0))
+    lo, hi = c.compute_range("manual")
+    assert lo == 0.0 and hi == 2.0
+    with pytest.raises(KeyError):
+        c.compute_range("nope")

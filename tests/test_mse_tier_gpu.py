@@ -138,3 +138,19 @@ def test_channel_two_tier_equals_all_exact_at_4096(cuda):
         p = (1.0 - best_i / 100.0).astype(np.float32)
         so, zo = O.qparams(p * np.minimum(lo, 0), p * np.maximum(hi, 0), qt, sym, False)
         assert np.array_equal(bits(s.cpu().numpy()), bits(np.asarray(so).reshape(-1))), qt
+
+
+@pytest.mark.parametrize("magnitude", [1e-9, 1e-11, 1e-13, 1e-15, 1e-25, 1e-36])
+def test_two_tier_small_magnitudes(cuda, magnitude):
+    """Quantization steps so small that |d|^2.4 leaves the range on which the approximation's error
+    bound was measured (|d| >= 1e-12; lg2.approx / ex2.approx flush denormals): the result must still
+    be the reference's, for the group kernels and the channel route alike."""
+    rng = np.random.default_rng(stable_seed("tiny", magnitude))
+    w = (rng.standard_normal((512, 128)) * magnitude).astype(np.float32)
+    wt = torch.from_numpy(w).to(cuda)
+    for qt, sym, strategy, gs in (("uint4", False, "group", 128), ("int4", True, "group", 64), ("int8", False, "group", 32),
+                                  ("int8", True, "channel", -1), ("uint4", False, "channel", -1)):
+        q, s, z = D.rtn_quantize(wt, qt, strategy, gs, sym, False, 1.0, True)
+        qo, so, zo = O.rtn_quantize(w, qt, strategy, gs, sym, False, 1.0, True)
+        assert np.array_equal(bits(s.cpu().numpy()), bits(np.asarray(so).reshape(-1))), (qt, strategy, magnitude)
+        assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8)), (qt, strategy, magnitude)
