@@ -353,7 +353,22 @@ def run_small_variants(torch, device, peak):
     gen = torch.Generator(device=device)
     gen.manual_seed(0)
     ws = [torch.randn((4096, 4096), generator=gen, device=device) * 0.02 for _ in range(2)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > L2 (126 MB)
+    flush = torch.zeros(128 << 20, dtype=torch.float32, device=device)   # 512 MB > L2 (126 MB)
+
+    def time_cold_ms(fn, iters=6):
+        """Median device time of fn with the L2 emptied before every iteration by READING the flush buffer
+        (clean lines: the timed kernels do not pay for somebody else's write-backs)."""
+        ts = []
+        for _ in range(iters):
+            flush.sum()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
 
     plan1 = D.RtnBatchPlan(ws, QuantType.QInt8, "tensor", -1, True, False, 1.0, False)   # the model's two weights
 
@@ -362,10 +377,15 @@ def run_small_variants(torch, device, peak):
 
     with dev.inputs_resident():          # the weights were resident before anything was launched
         ms = time_ms(cfg1)
+        ms_cold = time_cold_ms(cfg1)
     elts = sum(w.numel() for w in ws)
     out["cfg1_int8_sym_tensor"] = {
         "workload": "cfg1: RTN int8 symmetric per-tensor, 2 x (4096x4096) f32 (codes one byte per element)",
         "ms_per_step": ms, "value": 4 * elts / (ms * 1e-3) / 1e9, "unit": "GB/s",
+        "cache": "ms_per_step: iterations back to back — the two 64 MiB weights (128 MiB, L2 is 126 MB) partly "
+                 "survive in L2 from one iteration to the next; cold: L2 emptied by reading 512 MB before every iteration",
+        "cold": {"ms_per_step": ms_cold, "value": 4 * elts / (ms_cold * 1e-3) / 1e9, "unit": "GB/s",
+                 "roofline_frac": 5.0 * elts / (ms_cold * 1e-3) / 1e9 / peak},
         "roofline": {"bound": "hbm", "kernel": "minmax_partials_kernel + quantize_flat_kernel",
                      "achieved": 5.0 * elts / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 5.0 * elts / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_element": 5.0,

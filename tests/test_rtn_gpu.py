@@ -258,3 +258,21 @@ def test_tensor_mse_parallel_pairwise_matches_oracle(cuda, k, n):
     q, s, z = _product(w, "int8", "tensor", -1, True, False, 1.0, True)
     qo, so, zo = O.rtn_quantize(w, "int8", "tensor", -1, True, False, 1.0, True)
     assert np.array_equal(bits(s).reshape(-1), bits(so).reshape(-1)) and np.array_equal(as_i8(q, "int8"), as_i8(qo, "int8"))
+
+
+@pytest.mark.parametrize("qt,sym,clip,shape", [("int8", True, 1.0, (4096, 4096)), ("uint8", False, 0.9, (2048, 1024)),
+                                               ("int4", True, 1.0, (1200, 1028)), ("uint4", False, 0.8, (3000, 1500))])
+def test_per_tensor_route_on_large_weights_matches_oracle(cuda, qt, sym, clip, shape):
+    """TENSOR strategy on weights of 5 to 64 MB (cfg1's shape among them): the streamlined two-launch
+    route (min/max partials kept in L2, fold + parameters + vectorised codes walked back to front).
+    Codes, scale and zero point are the oracle's."""
+    from onnx_quantize_b200 import device_api as D
+    rng = np.random.default_rng(stable_seed(qt, shape))
+    w = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    w[17, 5] = 0.31                                        # the extremes sit in different slices
+    w[shape[0] - 3, shape[1] - 2] = -0.29
+    q, s, z = D.rtn_quantize(torch.from_numpy(w).to(cuda), qt, "tensor", -1, sym, False, clip, False)
+    qo, so, zo = O.rtn_quantize(w, qt, "tensor", -1, sym, False, clip, False)
+    assert np.array_equal(bits(s.cpu().numpy()), bits(np.asarray(so).reshape(-1)))
+    assert np.array_equal(z.cpu().numpy(), np.asarray(zo).reshape(-1).view(np.uint8))
+    assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8))
