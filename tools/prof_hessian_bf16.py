@@ -6,7 +6,7 @@ import torch
 from onnx_quantize_b200.hessian import hessian_accumulate
 
 one = "--one" in sys.argv
-shapes = [(32768, 4096)] if one else [(65536, 4096), (32768, 14336), (131072, 1152)]
+shapes = [(32768, 14336 if "--big" in sys.argv else 4096)] if one else [(65536, 4096), (32768, 14336), (131072, 1152)]
 chunks = [0] if one else [0, 1024, 2048, 4096, 8192, 16384, 32768]
 for (t, k) in shapes:
     g = torch.Generator(device="cuda"); g.manual_seed(0)
