@@ -14,9 +14,10 @@ weights generated on the device.  N > 1: every rank quantizes its own model-size
 Metric: GB/s of float32 weight consumed (4*K*N bytes / device time).  `value` = inputs resident in
 HBM; `e2e` = same work through the host-buffer API (pinned host weights -> H2D -> kernels -> D2H of
 codes/scales/zero points inside the timed region).  `roofline` is for the dominant kernel
-(rtn_group_fused_kernel<128, MSE>): algorithmic bytes 4.535 B/element vs the measured HBM copy
+(rtn_group_mse4_kernel<128>): algorithmic bytes 4.535 B/element vs the measured HBM copy
 bandwidth; the same pass without the MSE search (config 2a, clip_ratio 0.9 — the HBM-bound
-kernel) is reported under `variants`.
+kernel) is reported under `variants`, next to cfg1 / cfg3, the weight-sharding axis, GPTQ and the
+figures measured through the plugin seam (`e2e_plugin`).
 
 `--impl reference` times the CPU oracle port of the same path (NumPy, all host cores via a
 process pool over column slices) on a bounded sample of the workload.
@@ -856,7 +857,7 @@ def run_gpu_arm(args):
                      "frac": achieved / peak,
                      "traffic": 243.74e6,
                      "traffic_note": "dram__bytes_read+write of ONE 4096x14336 launch of the kernel (ncu --set full, "
-                                     "profiles/r1_prof_rtn_final_details.txt): 235.2 MB read = the f32 weight once, "
+                                     "profiles/r1_prof_rtn_final_details.txt; the kernel is unchanged since): 235.2 MB read = the f32 weight once, "
                                      "8.5 MB written (the rest of the 29 MB result is still in L2 at kernel end); "
                                      "algorithmic bytes of that launch: 266.3 MB",
                      "peak_source": peak_src,
@@ -875,13 +876,15 @@ def run_gpu_arm(args):
                              "the HBM-bound kernel of the same path is variants.cfg2a_no_mse"},
         "variants": {"cfg2a_no_mse_clip0.9": {
             "ms_per_step": ms_plain, "value": world * in_bytes / (ms_plain * 1e-3) / 1e9, "unit": "GB/s",
-            "roofline": {"bound": "hbm", "kernel": "rtn_group_nbits4_kernel<128>", "achieved": achieved_plain,
+            "roofline": {"bound": "hbm", "kernel": "rtn_group_nbits4_ring_kernel<128>", "achieved": achieved_plain,
                          "peak": peak, "unit": "GB/s", "frac": achieved_plain / peak,
-                         "traffic": 31.662e9,
-                         "traffic_note": "dram__bytes_read (27.954 GB = the f32 weights once) + dram__bytes_write "
-                                         "(3.708 GB = the packed results once) of the one batched launch over the "
-                                         "whole set, profiles/r1c_batch_stream_full_set.csv; algorithmic bytes of "
-                                         "that launch: 31.65 GB"}}},
+                         "launches_per_step": 2,
+                         "traffic": 17.922e9,
+                         "traffic_note": "the step is two launches of the persistent ring kernel (128 + 96 of the 224 jobs; "
+                                         "the tensor maps live in the kernel parameters).  ncu --set full on the FIRST launch "
+                                         "(profiles/r2_ring_stream_raw.csv): dram__bytes_read 15.806 GB + dram__bytes_write "
+                                         "2.116 GB = 17.92 GB against 17.90 GB of algorithmic bytes for its 128 matrices "
+                                         "(3.947 G elements x 4.535 B): no re-reads; DRAM 78.5 % of ncu's peak"}}},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_mse * 1e3,
         "clocks": sampler.summary() if sampler else None,

@@ -21,13 +21,14 @@ import zlib
 import numpy as np
 
 _store: dict[tuple[str, str], tuple] = {}
-_FINGERPRINT_SAMPLES = 1 << 16
+_FINGERPRINT_SAMPLES = 1 << 12
 
 
 def weight_fingerprint(array) -> str:
-    """Shape, dtype and a CRC-32 over a strided sample of ≤ 65 536 elements plus the first and
-    last 4 KiB — cheap next to the quantization of a weight large enough to be worth a pre-pass,
-    and it changes under any rescaling of rows or columns (what AWQ / SmoothQuant do)."""
+    """Shape, dtype and a CRC-32 over a strided sample of ≤ 4096 elements plus the first and last
+    4 KiB — 0.1 ms for a 235 MB weight (65 536 samples cost 1.5 ms, a third of the pre-pass route's
+    time over 2 x 224 fingerprints), and it changes under any rescaling of rows or columns (what AWQ
+    / SmoothQuant do)."""
     a = np.asarray(array)
     flat = a.reshape(-1) if a.flags.c_contiguous else np.ascontiguousarray(a).reshape(-1)
     step = max(1, flat.size // _FINGERPRINT_SAMPLES)
