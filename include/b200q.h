@@ -119,7 +119,10 @@ int b200q_rtn_quantize(const float* W, int64_t K, int64_t N, int qtype, int stra
 /* Many weights with one configuration in one call (a whole model's linear layers).  Semantically
  * a loop of b200q_rtn_quantize over `jobs`; the workspace is shared (sized for the largest job)
  * and the launches are issued back to back from C, so the host cost per weight is a few
- * microseconds instead of one foreign-function round trip. */
+ * microseconds instead of one foreign-function round trip.  The HBM-bound configuration (no
+ * search, uint4, MatMulNBits layout, group size 16 / 32 / 64 / 128, N % 16 == 0) goes out as ONE
+ * persistent launch per 128 jobs (job table + one TMA tensor map per weight in the kernel
+ * parameters, tiles handed out by a launch-wide counter that lives in the workspace). */
 typedef struct b200q_rtn_job {
   const float* W;        /* (K,N) row-major f32, device */
   int64_t K, N;
