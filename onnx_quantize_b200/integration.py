@@ -34,7 +34,8 @@ def patched_reference(ref):
     and ``_quantize_bias`` in ``qrules/_qlinear/gemm_to_qgemm.py`` (:3), and registers the calibrator
     class in the ``_CALIBRATORS`` table of ``core/_calibration/factory.py``.  Modules of the
     reference imported later pick the patched objects up from the defining modules.  Results
-    published by a multi-GPU pre-pass (``parallel.prequantized``) are dropped at exit."""
+    published by a multi-GPU pre-pass (``parallel.prequantized``) and the GPTQ plugin's device-side
+    calibration cache are dropped at exit."""
     from onnx_quantize_b200.parallel import prequantized
 
     prefix = ref.__name__ + "."
@@ -63,6 +64,9 @@ def patched_reference(ref):
         with prequantized.scope():
             yield
     finally:
+        from onnx_quantize_b200.core._algorithms.gptq import calibration_cache
+
+        calibration_cache.clear()                  # device Hessians / factors of the last calibration arrays
         for container, key, old in reversed(undo):
             if isinstance(container, dict):
                 container[key] = old
