@@ -276,3 +276,20 @@ def test_per_tensor_route_on_large_weights_matches_oracle(cuda, qt, sym, clip, s
     assert np.array_equal(bits(s.cpu().numpy()), bits(np.asarray(so).reshape(-1)))
     assert np.array_equal(z.cpu().numpy(), np.asarray(zo).reshape(-1).view(np.uint8))
     assert np.array_equal(q.cpu().numpy(), np.asarray(qo).view(np.uint8))
+
+
+def test_ring_kernel_against_the_fused_kernel_on_a_long_job_list(cuda):
+    """The persistent streaming kernel (TMA slab + registers, launch-wide tile dispenser) over 150 jobs —
+    two launches, thousands of tiles, every CTA walks many of them — against an independent route:
+    the plain fused kernel's (K,N) codes + parameters packed by `pack_matmul_nbits`."""
+    from onnx_quantize_b200 import device_api as D
+    g = torch.Generator(device=cuda)
+    g.manual_seed(5)
+    shapes = [(1024, 1024), (1024, 256), (1024, 3584), (3584, 1024), (512, 2064), (384, 1024)] * 25
+    ws = [torch.randn(s, device=cuda, generator=g) * 0.02 for s in shapes]
+    outs = D.rtn_quantize_batch(ws, "uint4", "group", 128, False, False, 0.9, False, layout="matmul_nbits")
+    for w, (b, s, z) in zip(ws, outs):
+        codes, s_kn, z_kn = D.rtn_quantize(w, "uint4", "group", 128, False, False, 0.9, False, layout="kn")
+        b_ref, z_ref = D.pack_matmul_nbits(codes, z_kn, 128, 4)
+        assert torch.equal(b, b_ref) and torch.equal(z, z_ref)
+        assert torch.equal(s.reshape(-1), s_kn)
