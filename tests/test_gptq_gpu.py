@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 QT = {"int4": q.QuantType.QInt4, "uint4": q.QuantType.QUInt4, "int8": q.QuantType.QInt8,
       "uint8": q.QuantType.QUInt8}
 PRECISIONS = ["fp32", "tf32x3"]
-FLIP_TOL = {"int4": 1e-3, "uint4": 1e-3, "int8": 5e-3, "uint8": 5e-3}
+FLIP_TOL = {"int4": 1e-3, "uint4": 1e-3, "int8": 5e-3, "uint8": 5e-3}   # see the module docstring for the 8-bit bound
 
 
 # ---- the dense product ---------------------------------------------------------------------------
@@ -229,14 +229,13 @@ def test_propagate_quality_and_parity(cuda, precision, qt, gs, sym, actorder):
     e_loop, e_loop_want = O.layer_output_rel_mse(x, w, deq), O.layer_output_rel_mse(x, w, want[3]["deq"])
     assert abs(e_loop - e_loop_want) <= 0.01 * e_loop_want, (e_loop, e_loop_want)
 
-    # (2) what the caller gets back: codes with the RE-DERIVED scale / zero point (gptq.py:219-231).
-    # For asymmetric types those no longer match the codes (a single flipped code at a group's
-    # extreme moves its re-derived range by 1/15), so the bar is 1 % symmetric, 3 % asymmetric.
+    # (2) what the caller gets back: codes with the RE-DERIVED scale / zero point (gptq.py:219-231):
+    # within 1 % of the oracle's as well (north_star), symmetric or not
     def rel(codes, s, z):
         return O.layer_output_rel_mse(x, w, O.dequantize_weight(np.asarray(codes), s, z, strategy, gs))
 
     e_got, e_want, e_ref = rel(*got), rel(*want[:3]), rel(*ref)
-    assert abs(e_got - e_want) <= (0.01 if sym else 0.03) * e_want, (e_got, e_want)
+    assert abs(e_got - e_want) <= 0.01 * e_want, (e_got, e_want)
     if sym:
         assert e_got < e_ref                            # real GPTQ beats the reference as written
 
@@ -267,11 +266,14 @@ def test_device_hessian_feeds_propagate_within_tolerance(cuda, hprec):
     got_codes = codes.cpu().numpy().view(np.int8)
     got_codes = np.where(got_codes > 7, got_codes - 16, got_codes)
     diff = np.abs(got_codes.astype(np.int32) - as_i8(want[0], "int4").astype(np.int32))
-    # a flipped code changes the error that is propagated down its column; with correlated channels
-    # (|U[i,j]/U[i,i]| > 1) the cascade can move a later element by two steps — seen for 1 element in
-    # 196 608 with either split mode, never with the fp32 Hessian
-    assert (diff != 0).mean() <= 1e-3 and diff.max() <= 2 and (diff > 1).mean() <= 2e-5, \
-        (diff.max(), (diff != 0).mean(), (diff > 1).mean())
+    # <= 0.1 % of the codes differ; every column's FIRST difference (rows run top to bottom) is a single
+    # step — a flipped code changes the error that is propagated down its column, and with correlated
+    # channels (|U[i,j]/U[i,i]| > 1) a later row of the SAME column can then move by two (see
+    # tests/test_gptq_bench_shapes_gpu.py: it happens with NumPy's own Hessian and an fp32 solve too)
+    assert (diff != 0).mean() <= 1e-3, (diff != 0).mean()
+    any_diff = diff != 0
+    cols = np.nonzero(any_diff.any(axis=0))[0]
+    assert (diff[np.argmax(any_diff, axis=0)[cols], cols] == 1).all()
     e, e_want = O.layer_output_rel_mse(x, w, deq.cpu().numpy()), O.layer_output_rel_mse(x, w, want[3]["deq"])
     assert abs(e - e_want) <= 0.01 * e_want, (e, e_want)
 
