@@ -14,6 +14,8 @@
 //   trtri : V^T = C^-T (lower) row block by row block:
 //           V^T[j, j] = (C_jj^-1)^T;  tmp = C[0:j, j]^T V^T[0:j, 0:j];  V^T[j, 0:j] = -(C_jj^-1)^T tmp
 // A non-positive or NaN pivot raises the status flag; U is then the identity (gptq.py:143-150).
+#include <stdlib.h>
+
 #include "dense.cuh"
 
 namespace b200q {
@@ -297,10 +299,23 @@ int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int ac
   B200Q_CUDA_OK(cudaMemsetAsync(ws.VT, 0, (size_t)K * K * 4, st));
 
   GemmTN g;
-  // ---- potrf (upper, right-looking) ----
+  // ---- potrf (upper) ----
+  // LEFT-looking by block rows: before block row j is factored it is brought up to date with ONE product
+  // over all finished rows, A[j, j:] -= C[0:j, j]^T C[0:j, j:] (contraction j * 128, output 128 x rest).
+  // The right-looking form (a rank-128 update of the whole trailing matrix after every block row) reads
+  // AND writes the trailing matrix 112 times at K = 14336 — 61 GB of read-modify-write traffic, the bulk
+  // of the factor's GEMM time; this form only reads the finished rows (30 GB) and writes each block row
+  // once.  B200Q_CHOL_RIGHT=1 keeps the right-looking loop (A/B measurements).
+  static int right_looking = -1;
+  if (right_looking < 0) { const char* e = getenv("B200Q_CHOL_RIGHT"); right_looking = (e && e[0] == '1') ? 1 : 0; }
   for (int64_t j0 = 0, jb = 0; j0 < K; j0 += kNB, ++jb) {
     const int nb = (int)(K - j0 < kNB ? K - j0 : kNB);
     float* DIj = ws.DI + jb * kNB * kNB;
+    if (!right_looking && j0 > 0) {
+      g = GemmTN{ws.Hr + j0, K, ws.Hr + j0, K, ws.Hr + j0 * K + j0, K, j0, nb, K - j0, -1.0f, 1, 0, 0, precision};
+      int rc = gemm_tn(g, st);
+      if (rc != B200Q_OK) return rc;
+    }
     chol_diag_kernel<<<1, 256, 0, st>>>(ws.Hr, K, j0, nb, DIj, status, ws.diag, perm, ws.damp,
                                         precision == B200Q_FP32_SIMT ? 0.0f : kMarginalPivot);
     B200Q_LAUNCH_OK();
@@ -313,10 +328,11 @@ int b200q_hinv_cholesky_upper(const float* H, int64_t K, double percdamp, int ac
     if (rc != B200Q_OK) return rc;
     B200Q_CUDA_OK(cudaMemcpy2DAsync(P, (size_t)K * 4, ws.tmp, (size_t)K * 4, (size_t)rest * 4, nb,
                                     cudaMemcpyDeviceToDevice, st));
-    // trailing update, upper triangle only
-    g = GemmTN{P, K, P, K, ws.Hr + (j0 + nb) * K + (j0 + nb), K, nb, rest, rest, -1.0f, 1, 1, 0, precision};
-    rc = gemm_tn(g, st);
-    if (rc != B200Q_OK) return rc;
+    if (right_looking) {   // trailing update, upper triangle only
+      g = GemmTN{P, K, P, K, ws.Hr + (j0 + nb) * K + (j0 + nb), K, nb, rest, rest, -1.0f, 1, 1, 0, precision};
+      rc = gemm_tn(g, st);
+      if (rc != B200Q_OK) return rc;
+    }
   }
   // ---- trtri: VT = C^-T, row block by row block ----
   for (int64_t j0 = 0, jb = 0; j0 < K; j0 += kNB, ++jb) {
