@@ -28,6 +28,35 @@ def test_assign_units_balances_the_llama_set():
     assert S.assign_units([5.0], 4)[0] == [0]
 
 
+def test_exchange_plan_groups_one_unit_per_owner():
+    from onnx_quantize_b200.parallel.gptq_pipeline import exchange_plan
+
+    ks, costs = [], []
+    for _ in range(32):
+        for k, n in LLAMA_LAYER:
+            ks.append(k)
+            costs.append(k ** 3 * 2.0 / 3 + k * k * n)
+    order = sorted(range(len(ks)), key=lambda i: (-costs[i], i))
+    for ranks in (1, 2, 4, 8):
+        owners = [None] * len(ks)
+        for r, idxs in enumerate(S.assign_units(costs, ranks)):
+            for i in idxs:
+                owners[i] = r
+        plan = exchange_plan(ks, order, owners, ranks)
+        assert sorted(i for ex in plan for i in ex) == list(range(len(ks)))     # every unit exactly once
+        for ex in plan:
+            assert len(ex) in (1, ranks)
+            if len(ex) > 1:                                  # one size, entry r owned by rank r
+                assert len({ks[i] for i in ex}) == 1 and [owners[i] for i in ex] == list(range(ranks))
+        firsts = [order.index(ex[0]) for ex in plan]
+        assert firsts == sorted(firsts)                      # steps start in longest-solve-first order
+        if ranks > 1:
+            assert sum(len(ex) > 1 for ex in plan) >= len(ks) // ranks - 4
+    # sizes that never line up fall back to single reduces; an owner without a unit of a size blocks its group
+    assert exchange_plan([256, 512, 384], [1, 2, 0], [0, 1, 0], 2) == [[1], [2], [0]]
+    assert exchange_plan([512, 512, 512], [0, 1, 2], [0, 0, 1], 2) == [[0, 2], [1]]
+
+
 def test_shard_batches_round_robin():
     assert C.shard_batches(10, 0, 4) == [0, 4, 8] and C.shard_batches(10, 3, 4) == [3, 7]
     assert sorted(sum((C.shard_batches(10, r, 4) for r in range(4)), [])) == list(range(10))

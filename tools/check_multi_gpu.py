@@ -47,7 +47,8 @@ for qt, strategy, gs, sym, mse in (("uint4", "group", 128, False, True), ("int8"
 # ---- 2. GPTQ pipeline ----------------------------------------------------------------------------
 rng = np.random.default_rng(1)
 units_np = []
-for u, (k, ns) in enumerate(((512, (256, 128)), (256, (384,)), (384, (128, 128, 64)))):
+for u, (k, ns) in enumerate(((512, (256, 128)), (256, (384,)), (384, (128, 128, 64)), (512, (128, 64)),
+                             (256, (256,)), (512, (64,)), (512, (256, 64)))):
     x = (rng.standard_normal((16, 64, k)) * rng.uniform(0.5, 2.0, k)).astype(np.float32)     # 16 samples
     units_np.append((f"u{u}", k, x, [(rng.standard_normal((k, n)) * 0.05).astype(np.float32) for n in ns]))
 per = 16 // world
@@ -55,6 +56,13 @@ units = [GptqUnit(name, k, [torch.from_numpy(w).to(device) for w in ws],
                   torch.from_numpy(x[rank * per:(rank + 1) * per].reshape(-1, k)).to(device), 16)
          for name, k, x, ws in units_np]
 run = GptqPipeline(4, device).run(units, GptqSpec("int4", "group", 128, True, mode="propagate", precision="bf16x3"))
+if rank == 0:
+    from onnx_quantize_b200.parallel.gptq_pipeline import exchange_plan
+    costs = [u.solve_cost() for u in units]
+    order = sorted(range(len(units)), key=lambda i: (-costs[i], i))
+    plan = exchange_plan([u.k for u in units], order, [run.owner[u.name] for u in units], world)
+    print(f"exchange steps: {[[units[i].name for i in ex] for ex in plan]} "
+          f"({sum(len(ex) > 1 for ex in plan)} reduce-scatter, {sum(len(ex) == 1 for ex in plan)} reduce)", flush=True)
 torch.cuda.synchronize()
 for name, k, x, ws in units_np:
     owner = run.owner[name]
