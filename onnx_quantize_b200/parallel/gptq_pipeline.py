@@ -140,6 +140,9 @@ class GptqPipeline:
 
     def run(self, units: Sequence[GptqUnit], spec: GptqSpec) -> GptqRun:
         rank, n_ranks = world()
+        if self.group is not None and n_ranks > 1 and dist.get_world_size(self.group) != n_ranks:
+            # owners are global ranks (`dist.reduce(dst=...)`) and slice r of a stacked buffer belongs to rank r
+            raise ValueError("GptqPipeline needs a process group that spans all ranks")
         costs = [u.solve_cost() for u in units]
         plan = assign_units(costs, n_ranks)
         out = GptqRun()
