@@ -304,9 +304,10 @@ def run_gptq_variant(args, torch, dist, device, world, rank, model="llama3_8b", 
         "extrapolation": f"x{model_layers / layers:g}: the {model_layers} layers are identical in shape",
         "hessian_s": hess_ms * 1e-3, "solve_s": solve_ms * 1e-3,
         "hessian_reduce_s_under_solves": red_ms * 1e-3,
-        "phases": "hessian_s = every unit's Hessian on this rank's tokens; then the NCCL reduces to the owners run on "
+        "phases": "hessian_s = every unit's Hessian on this rank's tokens; then the partial Hessians reach the owners "
+                  "(in-place NCCL reduce-scatters over stacked buffers, one unit per owner each; plain reduces for leftovers) on "
                   "a communication stream UNDERNEATH the solves (each solve waits for its own unit's reduce only): "
-                  "solve_s spans both, hessian_reduce_s_under_solves is when the last reduce finished",
+                  "solve_s spans both, hessian_reduce_s_under_solves is when the last exchange step finished",
         "factorizations_failed": n_failed,
         "hessian_tflops_algorithmic": flops / (hess_ms * 1e-3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": "hessian_bf16x3_kernel" if is_bf16 else "hessian_kernel",
