@@ -1,3 +1,5 @@
+"""Hessian kernel against a closed-form pattern (H[i][j] = (T/8)(i+1)(j+1)) and random data at small
+shapes: the first thing to run when a tensor-map / swizzle / descriptor change breaks the contraction."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
