@@ -1,4 +1,4 @@
-"""The whole Llama-3-8B-shaped set through ONE launch of rtn_group_nbits4_batch_kernel (cfg2a), for
+"""The whole Llama-3-8B-shaped set through the batched RTN entry point (cfg2a: two launches of rtn_group_nbits4_ring_kernel; round 1: one launch of the batch kernel it replaced), for
 ncu: how much DRAM traffic does the launch really cause, and how busy is DRAM?"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
