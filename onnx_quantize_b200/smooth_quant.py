@@ -5,7 +5,6 @@ node, the initializer swap) stays the reference's; this module returns the array
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from onnx_quantize_b200 import _device as dev
