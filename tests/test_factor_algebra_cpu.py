@@ -57,3 +57,41 @@ def test_left_looking_blocked_cholesky_is_the_cholesky_factor(k, nb):
     h = _spd(k, stable_seed("left_looking", k, nb))
     c = _left_looking_upper_cholesky(h, nb)
     assert np.allclose(c, np.linalg.cholesky(h).T, rtol=1e-10, atol=1e-12)
+
+
+def _gptq_float64(w, u, block, left_looking):
+    """GPTQ's block loop (gptq.py:153-208 with the transposed, non-zero triangle of U) in float64 with a
+    fixed symmetric 4-bit grid per 16-row group — right-looking as the reference writes it (every
+    finished block pushed into ALL later rows at once) or left-looking as csrc/gptq.cu runs it (a
+    block's rows brought up to date right before the block, from the stored error rows)."""
+    k, n = w.shape
+    w = w.copy()
+    codes = np.zeros((k, n), dtype=np.int64)
+    err = np.zeros((k, n))
+    scale = None
+    for i1 in range(0, k, block):
+        i2 = min(i1 + block, k)
+        if left_looking and i1:
+            w[i1:i2] -= u[:i1, i1:i2].T @ err[:i1]
+        for i in range(i1, i2):
+            if i % 16 == 0:
+                scale = np.maximum(np.abs(w[i:i + 16]).max(axis=0), 1e-9) / 7.0
+            q = np.clip(np.rint(w[i] / scale), -7, 7)
+            codes[i] = q
+            err[i] = (w[i] - q * scale) / u[i, i]
+            w[i + 1:i2] -= np.outer(u[i, i + 1:i2], err[i])
+        if not left_looking and i2 < k:
+            w[i2:] -= u[i1:i2, i2:].T @ err[i1:i2]
+    return codes, err
+
+
+@pytest.mark.parametrize("k,block", [(64, 16), (96, 32), (80, 32)])
+def test_left_looking_propagation_is_the_same_loop(k, block):
+    rng = np.random.default_rng(stable_seed("left_looking_gptq", k, block))
+    h = _spd(k, stable_seed("left_looking_gptq_h", k))
+    u = np.linalg.cholesky(np.linalg.inv(h)).T
+    w = rng.standard_normal((k, 24)) * 0.05
+    c_right, e_right = _gptq_float64(w, u, block, left_looking=False)
+    c_left, e_left = _gptq_float64(w, u, block, left_looking=True)
+    assert np.array_equal(c_right, c_left)
+    assert np.allclose(e_right, e_left, rtol=1e-9, atol=1e-12)
